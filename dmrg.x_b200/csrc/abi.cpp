@@ -1,0 +1,230 @@
+/*  abi.cpp — extern "C" surface declared in include/dmrgx.h.  Thin: argument marshalling, status codes,
+ *  no exception crosses the boundary. */
+#include <cstring>
+#include <string>
+
+#include "../../include/dmrgx.h"
+#include "common.h"
+
+using namespace dmrgx;
+
+namespace {
+thread_local std::string g_msg;
+template <class F>
+int guard(F&& f) {
+    try { f(); return 0; }
+    catch (const Err& e) { g_msg = e.what(); return e.code ? e.code : 1; }
+    catch (const std::exception& e) { g_msg = e.what(); return 1; }
+    catch (...) { g_msg = "unknown error"; return 1; }
+}
+inline Ctx* C(dmrgx_ctx c) { return (Ctx*)c; }
+inline Block* B(dmrgx_block b) { return (Block*)b; }
+inline Kron* K(dmrgx_kron k) { return (Kron*)k; }
+inline HShell* H(dmrgx_hshell h) { return (HShell*)h; }
+inline XForm* X(dmrgx_xform x) { return (XForm*)x; }
+std::vector<Term> terms_of(dmrgx_int n, const double* a, const int* iop, const dmrgx_int* isite, const int* jop, const dmrgx_int* jsite) {
+    std::vector<Term> t;
+    for (dmrgx_int i = 0; i < n; ++i) t.push_back({a[i], iop[i], isite[i], jop[i], jsite[i]});
+    return t;
+}
+}  // namespace
+
+extern "C" {
+
+const char* dmrgx_last_error(void) { return g_msg.c_str(); }
+dmrgx_int dmrgx_launch_count(void) { return dev::launch_count(); }
+
+int dmrgx_ctx_create(int device, void* stream, dmrgx_ctx* out) {
+    *out = nullptr;
+    dev::Stream* st = nullptr;
+    int e = dev::init(device, stream, &st);
+    if (e) { g_msg = dev::last_error(); return e; }
+    Ctx* c = new Ctx();
+    c->st = st;
+    *out = (dmrgx_ctx)c;
+    return 0;
+}
+int dmrgx_ctx_destroy(dmrgx_ctx ctx) { if (!ctx) return 0; return guard([&] { dev::destroy(C(ctx)->st); delete C(ctx); }); }
+int dmrgx_ctx_sync(dmrgx_ctx ctx) { return guard([&] { dev::sync(C(ctx)->st); }); }
+int dmrgx_ctx_set_dense_threshold(dmrgx_ctx ctx, double fill) { C(ctx)->dense_fill_threshold = fill; return 0; }
+
+int dmrgx_block_create(dmrgx_ctx ctx, dmrgx_int nsites, dmrgx_int nsectors, const double* qn, const dmrgx_int* sz, dmrgx_block* out) {
+    *out = nullptr;
+    return guard([&] {
+        *out = (dmrgx_block)block_from_csr_begin(C(ctx), (int)nsites, std::vector<double>(qn, qn + nsectors), std::vector<long long>(sz, sz + nsectors));
+    });
+}
+int dmrgx_block_single_site(dmrgx_ctx ctx, int spin_twice, dmrgx_block* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_block)block_single_site(C(ctx), spin_twice); });
+}
+int dmrgx_block_set_operator(dmrgx_block blk, int op, dmrgx_int isite, const dmrgx_int* rowptr, const dmrgx_int* colidx, const double* values) {
+    return guard([&] { block_set_operator(B(blk), op, (int)isite, rowptr, colidx, values); });
+}
+int dmrgx_block_get_operator(dmrgx_block blk, int op, dmrgx_int isite, dmrgx_int* nnz, dmrgx_int* rowptr, dmrgx_int* colidx, double* values) {
+    return guard([&] {
+        std::vector<long long> rp, ci;
+        std::vector<double> vv;
+        block_get_operator(B(blk), op, (int)isite, rp, ci, vv);
+        if (nnz) *nnz = (dmrgx_int)ci.size();
+        if (colidx) {
+            std::copy(rp.begin(), rp.end(), rowptr);
+            std::copy(ci.begin(), ci.end(), colidx);
+            std::copy(vv.begin(), vv.end(), values);
+        }
+    });
+}
+int dmrgx_block_info(dmrgx_block blk, dmrgx_int* nsites, dmrgx_int* nstates, dmrgx_int* nsectors) {
+    *nsites = B(blk)->nsites; *nstates = B(blk)->sec.nstates(); *nsectors = B(blk)->sec.nsec();
+    return 0;
+}
+int dmrgx_block_sectors(dmrgx_block blk, double* qn, dmrgx_int* sz) {
+    const Sectors& s = B(blk)->sec;
+    for (int i = 0; i < s.nsec(); ++i) { qn[i] = s.qn[i]; sz[i] = s.size[i]; }
+    return 0;
+}
+int dmrgx_block_check(dmrgx_block blk) { return guard([&] { block_check(B(blk)); }); }
+int dmrgx_block_destroy(dmrgx_block blk) { return guard([&] { delete B(blk); }); }
+int dmrgx_block_enlarge(dmrgx_block left, dmrgx_block site, dmrgx_int nterms, const double* a, const int* iop, const dmrgx_int* isite,
+                        const int* jop, const dmrgx_int* jsite, dmrgx_block* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_block)block_enlarge(B(left), B(site), terms_of(nterms, a, iop, isite, jop, jsite)); });
+}
+
+int dmrgx_kron_create(dmrgx_block left, dmrgx_block right, dmrgx_int nqn, const double* qn, dmrgx_kron* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_kron)kron_create(B(left), B(right), std::vector<double>(qn, qn + nqn)); });
+}
+int dmrgx_kron_destroy(dmrgx_kron k) { return guard([&] { delete K(k); }); }
+dmrgx_int dmrgx_kron_size(dmrgx_kron k) { return (dmrgx_int)K(k)->pairs.size(); }
+dmrgx_int dmrgx_kron_num_states(dmrgx_kron k) { return K(k)->nstates(); }
+int dmrgx_kron_data(dmrgx_kron k, double* qn, dmrgx_int* li, dmrgx_int* ri, dmrgx_int* sizes, dmrgx_int* offsets) {
+    const Kron* kk = K(k);
+    for (size_t p = 0; p < kk->pairs.size(); ++p) { qn[p] = kk->pairs[p].qn; li[p] = kk->pairs[p].il; ri[p] = kk->pairs[p].ir; sizes[p] = kk->pairs[p].size; }
+    for (size_t p = 0; p < kk->off.size(); ++p) offsets[p] = kk->off[p];
+    return 0;
+}
+dmrgx_int dmrgx_kron_map(dmrgx_kron k, dmrgx_int l, dmrgx_int r) { return K(k)->find((int)l, (int)r); }
+dmrgx_int dmrgx_kron_offsets_lr(dmrgx_kron k, dmrgx_int l, dmrgx_int r) { int p = K(k)->find((int)l, (int)r); return p < 0 ? -1 : K(k)->off[p]; }
+
+int dmrgx_hshell_create(dmrgx_kron k, dmrgx_int nterms, const double* a, const int* iop, const dmrgx_int* isite, const int* jop,
+                        const dmrgx_int* jsite, dmrgx_hshell* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_hshell)hshell_create(K(k), terms_of(nterms, a, iop, isite, jop, jsite)); });
+}
+int dmrgx_hshell_create_single(dmrgx_kron k, int opl, dmrgx_int il, int opr, dmrgx_int ir, dmrgx_hshell* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_hshell)hshell_create_single(K(k), opl, (int)il, opr, (int)ir); });
+}
+int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y) { return guard([&] { hshell_apply(H(h), d_x, d_y); }); }
+int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
+    return guard([&] {
+        HShell* s = H(h);
+        Ctx* ctx = s->ctx;
+        const size_t bytes = (size_t)s->n * 8;
+        if (!s->xbuf) {
+            s->xbuf = std::make_shared<DevBuf>(ctx, bytes);
+            s->ybuf = std::make_shared<DevBuf>(ctx, bytes);
+        }
+        dev::h2d(ctx->st, s->xbuf->p, x, bytes);
+        hshell_apply(s, s->xbuf->as<double>(), s->ybuf->as<double>());
+        dev::d2h(ctx->st, y, s->ybuf->p, bytes);
+        dev::sync(ctx->st);
+    });
+}
+int dmrgx_hshell_destroy(dmrgx_hshell h) { return guard([&] { if (h) { dev::sync(H(h)->ctx->st); delete H(h); } }); }
+int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, double* alg_bytes, double* alg_flops, dmrgx_int* nt1, dmrgx_int* nt2) {
+    HShell* s = H(h);
+    if (nstates) *nstates = s->n;
+    if (nterms) *nterms = s->nterms;
+    if (alg_bytes) *alg_bytes = (double)s->alg_bytes;
+    if (alg_flops) *alg_flops = s->alg_flops;
+    if (nt1) *nt1 = (dmrgx_int)s->stage1.items.size();
+    if (nt2) *nt2 = (dmrgx_int)s->stage2.items.size();
+    return 0;
+}
+
+int dmrgx_eigs_smallest(dmrgx_hshell h, const dmrgx_eigs_opts* opts, double* e0, double* d_psi, dmrgx_eigs_stats* stats) {
+    return guard([&] {
+        EigsOpts o;
+        if (opts) { o.tol = opts->tol; o.ncv = (int)opts->ncv; o.max_it = (int)opts->max_it; o.seed = opts->seed; }
+        if (o.tol <= 0) o.tol = 1e-8;
+        if (o.ncv <= 0) o.ncv = 16;
+        EigsStats s;
+        *e0 = eigs_smallest(H(h), o, d_psi, &s);
+        if (stats) { stats->nmatvec = s.nmatvec; stats->nrestart = s.nrestart; stats->converged = s.converged; stats->resid = s.resid; }
+    });
+}
+
+int dmrgx_truncate(dmrgx_kron k, const double* d_psi, dmrgx_int mstates, dmrgx_xform* left, dmrgx_xform* right) {
+    *left = nullptr; *right = nullptr;
+    return guard([&] {
+        XForm *l, *r;
+        truncate(K(k), d_psi, mstates, &l, &r);
+        *left = (dmrgx_xform)l; *right = (dmrgx_xform)r;
+    });
+}
+int dmrgx_xform_info(dmrgx_xform x, dmrgx_int* m, dmrgx_int* nstates, dmrgx_int* nsectors, double* trunc_err, dmrgx_int* nspec) {
+    const XForm* f = X(x);
+    if (m) *m = f->newsec.nstates();
+    if (nstates) *nstates = f->nstates_old;
+    if (nsectors) *nsectors = f->newsec.nsec();
+    if (trunc_err) *trunc_err = f->trunc_err;
+    if (nspec) *nspec = (dmrgx_int)f->spec_eig.size();
+    return 0;
+}
+int dmrgx_xform_sectors(dmrgx_xform x, double* qn, dmrgx_int* sz) {
+    const Sectors& s = X(x)->newsec;
+    for (int i = 0; i < s.nsec(); ++i) { qn[i] = s.qn[i]; sz[i] = s.size[i]; }
+    return 0;
+}
+int dmrgx_xform_spectrum(dmrgx_xform x, double* eigval, dmrgx_int* blk) {
+    const XForm* f = X(x);
+    for (size_t i = 0; i < f->spec_eig.size(); ++i) { eigval[i] = f->spec_eig[i]; blk[i] = f->spec_blk[i]; }
+    return 0;
+}
+int dmrgx_xform_rotmat(dmrgx_xform x, double* out) {
+    return guard([&] {
+        const XForm* f = X(x);
+        const long long m = f->newsec.nstates(), n = f->nstates_old;
+        std::memset(out, 0, sizeof(double) * m * n);
+        for (int k = 0; k < f->newsec.nsec(); ++k) {
+            const int mk = f->newsec.size[k], nk = f->old_size[k];
+            std::vector<double> u((size_t)mk * nk);
+            dev::d2h(f->ctx->st, u.data(), f->U[k]->p, u.size() * 8);
+            dev::sync(f->ctx->st);
+            for (int i = 0; i < mk; ++i)
+                std::memcpy(out + (size_t)(f->newsec.off[k] + i) * n + f->old_off[k], u.data() + (size_t)i * nk, sizeof(double) * nk);
+        }
+    });
+}
+int dmrgx_xform_destroy(dmrgx_xform x) { return guard([&] { delete X(x); }); }
+
+int dmrgx_rotate(dmrgx_block enlarged, dmrgx_xform x, dmrgx_block* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_block)rotate(B(enlarged), X(x)); });
+}
+
+int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value) {
+    return guard([&] {
+        HShell* s = H(h1);
+        Ctx* ctx = s->ctx;
+        BufRef y = std::make_shared<DevBuf>(ctx, (size_t)s->n * 8 + 8);
+        hshell_apply(s, d_psi, y->as<double>());
+        double* d_out = y->as<double>() + s->n;
+        dev::dot(ctx->st, d_psi, y->as<double>(), s->n, d_out);
+        dev::d2h(ctx->st, value, d_out, 8);
+        dev::sync(ctx->st);
+    });
+}
+
+int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out) { return guard([&] { *d_out = (double*)dev::malloc_bytes(C(ctx)->st, (size_t)n * 8); }); }
+int dmrgx_vec_free(dmrgx_ctx ctx, double* d) { return guard([&] { dev::free_bytes(C(ctx)->st, d); }); }
+int dmrgx_vec_set(dmrgx_ctx ctx, double* d_dst, const double* h_src, dmrgx_int n) {
+    return guard([&] { dev::h2d(C(ctx)->st, d_dst, h_src, (size_t)n * 8); dev::sync(C(ctx)->st); });
+}
+int dmrgx_vec_get(dmrgx_ctx ctx, double* h_dst, const double* d_src, dmrgx_int n) {
+    return guard([&] { dev::d2h(C(ctx)->st, h_dst, d_src, (size_t)n * 8); dev::sync(C(ctx)->st); });
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+/*  dev.h — the thin device layer.  Everything above it (block.cpp, kron.cpp, hshell.cpp, eigs.cpp,
+ *  truncate.cpp, abi.cpp) is plain C++ that plans work on the host and hands flat POD work lists
+ *  to the sm_100a kernels in dev_cuda.cu through the functions declared here.
+ *
+ *  The product library libdmrgx_b200.so links dev_cuda.cu and nothing else behind this interface; there
+ *  is no CPU implementation in the product.  (tests/plancheck/dev_host.cpp re-implements this header
+ *  with naive host loops ONLY so that `pytest -m "not gpu"` can check the host-side planning logic —
+ *  offsets, strides, sector maps — in a container without a GPU; it is never part of the product.)
+ */
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace dev {
+
+/* ------------------------------------------------------------------------------------------------
+ *  The one compute engine: every contraction of the hot path is a list of output tiles ("work
+ *  items"), each accumulating a chain of segments in registers and writing its tile exactly once.
+ *      GEMM  : acc(m,n) += coef * Σ_k A(m,k) · B(k,n)      A(m,k)=A[m*lda_m+k*lda_k], B(k,n)=B[n*ldb_n+k*ldb_k]
+ *      AXPY  : acc(m,n) += coef * A(m,n)                    (n uses lda_k as its stride)
+ *      DIAG  : acc(m,n) += coef * [m + drow == n]
+ *      CSRA  : acc(m,n) += coef * Σ_{e in row (row0+m)} val[e] · B(colidx[e], n)      (sparse left factor)
+ *      CSRB  : acc(m,n) += coef * Σ_{e in row (row0+n)} val[e] · A(m, colidx[e])      (sparse right factor)
+ *      CSRADD: acc(m,n) += coef * Σ_{e in row (row0+m)} val[e] · [colidx[e] == n + dcol]
+ *  Fast (FP64 DMMA) GEMM layouts: lda_k==1 or lda_m==1, and ldb_k==1 or ldb_n==1.
+ *  Pointer fields of the sparse segments: B = CSR values; A = the dense operand — for CSRA the right
+ *  factor addressed with (ldb_k, ldb_n), for CSRB the left factor addressed with (lda_m, lda_k).
+ * ---------------------------------------------------------------------------------------------- */
+enum SegType : int { SEG_GEMM = 0, SEG_AXPY = 1, SEG_DIAG = 2, SEG_CSRA = 3, SEG_CSRB = 4, SEG_CSRADD = 5 };
+
+struct Segment {
+    const double* A;
+    const double* B;      /* CSR*: values */
+    const int* rowptr;    /* CSR* */
+    const int* colidx;    /* CSR*: indices local to the tile the CSR block describes */
+    long long lda_m, lda_k;
+    long long ldb_n, ldb_k;
+    double coef;
+    int K;
+    int type;
+    int row0;             /* CSR row that corresponds to row 0 (CSRA/CSRADD) or column 0 (CSRB) of the cell */
+    int d;                /* DIAG: drow; CSRADD: dcol */
+    int flags;            /* SEGF_A_X / SEGF_B_X: the pointer field holds a BYTE OFFSET into the x vector of the launch */
+    int pad;
+};
+enum : int { SEGF_A_X = 1, SEGF_B_X = 2 };
+
+struct WorkItem {
+    double* C;            /* tile origin */
+    long long ldc;
+    int m0, n0;           /* origin of the tile inside its cell: operand bases are A + m0*lda_m, B + n0*ldb_n */
+    int tm, tn;           /* extents, 1..TILE */
+    int seg_begin, seg_end;
+    int mode;             /* 0: store (C = acc), 1: atomic accumulate (C += acc) */
+    int c_in_y;           /* 1: C holds a BYTE OFFSET into the y vector of the launch */
+};
+
+constexpr int TILE = 64;  /* maximum tile extent of a work item */
+
+struct Stream;            /* device, stream, solver handle */
+
+int init(int device, void* user_stream, Stream** out); /* 0 on success; fails loudly without a CUDA device */
+void destroy(Stream*);
+const char* last_error();
+int device_of(Stream*);
+void* raw_stream(Stream*);
+
+void* malloc_bytes(Stream*, size_t bytes);
+void free_bytes(Stream*, void* p);
+void* malloc_pinned(size_t bytes);
+void free_pinned(void* p);
+void h2d(Stream*, void* dst, const void* src, size_t bytes);
+void d2h(Stream*, void* dst, const void* src, size_t bytes);
+void d2d(Stream*, void* dst, const void* src, size_t bytes);
+void memset0(Stream*, void* dst, size_t bytes);
+void sync(Stream*);
+/* number of kernel launches issued through this layer so far (bench.py's gpu_launches) */
+long long launch_count();
+
+/* chain contraction engine */
+/* x / y: base pointers that offset-typed operands (SEGF_*_X, c_in_y) are relative to, so one plan serves any
+   pair of device vectors (the Lanczos basis vectors change every step; the plan does not). */
+void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y);
+
+/* vector kernels of the thick-restart Lanczos (all results stay on the device) */
+void fill_random(Stream*, double* x, long long n, unsigned long long seed);
+void multidot(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, double* d_out);
+/* w -= Σ_i d_coef[i] V_i ; if d_dots2: d_dots2[i] = V_i·w_new (fused second Gram-Schmidt pass);
+   if d_nrm2: *d_nrm2 = ||w_new||²  */
+void multiaxpy(Stream*, const double* V, long long ldv, int nvec, const double* d_coef, double* w, long long n, double* d_dots2,
+               double* d_nrm2);
+/* v = w / sqrt(*d_nrm2) */
+void scale_inv_norm(Stream*, const double* w, const double* d_nrm2, double* v, long long n);
+/* in place: V_a <- Σ_i S[i*kk+a] V_i  (i < ncv, a < kk), S on the device */
+void ritz_rotate(Stream*, double* V, long long ldv, long long n, int ncv, const double* d_S, int kk);
+void dot(Stream*, const double* x, const double* y, long long n, double* d_out);
+void scal(Stream*, double* x, long long n, double a);
+
+/* dense symmetric eigendecomposition of an n×n block (in place): on exit row k of A (row-major) is the
+   k-th eigenvector, eigenvalues ascending in d_w */
+int syevd(Stream*, int n, double* d_A, double* d_w);
+/* dst[k][:] = src[(n-1-k)][:], k < m   (the m largest eigenvectors, descending) */
+void gather_rows_reversed(Stream*, const double* src, int n, int m, double* dst);
+/* |x_i| < tol -> 0 */
+void filter_small(Stream*, double* x, long long n, double tol);
+/* out[i] = a[i] + alpha*b[i] (a may be null -> alpha*b) */
+void axpby_out(Stream*, const double* a, const double* b, double alpha, double* out, long long n);
+
+}  // namespace dev

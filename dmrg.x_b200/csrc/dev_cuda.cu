@@ -1,0 +1,522 @@
+/*  dev_cuda.cu — hand-written sm_100a kernels behind dev.h.
+ *
+ *  Hot kernel: chain_kernel — one CTA per 64×64 (or smaller) output tile, 4 warps in a 2×2 grid, each
+ *  warp a 32×32 sub-tile held as 4×4 FP64 DMMA (mma.sync.m8n8k4.f64) accumulator fragments.  Operand
+ *  chunks of 16 in K are staged global→shared with cp.async (LDGSTS.64, zero-filled at the ragged
+ *  edges), double-buffered; the shared layouts are padded (row stride ≡ 4 mod 16 doubles) so that both
+ *  the row-major and the transposed fragment reads are bank-conflict-free.  FP64 has no tcgen05/UMMA
+ *  kind, so DMMA through mma.sync is the Blackwell tensor path for this arithmetic.
+ *  Sparse (CSR) and scaled-identity factors are accumulated into the same register tile by the
+ *  coalesced slow-path segments, so every output element is written exactly once per launch.
+ */
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dev.h"
+
+namespace dev {
+
+static thread_local std::string g_err;
+static long long g_launches = 0;
+const char* last_error() { return g_err.c_str(); }
+long long launch_count() { return g_launches; }
+
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char buf_[512];                                                                             \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            g_err = buf_;                                                                               \
+            fprintf(stderr, "[dmrgx] %s\n", buf_);                                                      \
+            throw std::runtime_error(buf_);                                                             \
+        }                                                                                               \
+    } while (0)
+
+struct Stream {
+    int device = 0;
+    cudaStream_t s = nullptr;
+    bool own = false;
+    cusolverDnHandle_t solver = nullptr;
+    double* partials = nullptr; /* deterministic two-stage reductions */
+    int* info = nullptr;
+    void* solver_work = nullptr;
+    size_t solver_work_bytes = 0;
+    int num_sms = 148;
+};
+
+constexpr int RED_BLOCKS = 592; /* 148 SMs × 4 resident CTAs */
+constexpr int RED_MAXVEC = 40;
+
+int init(int device, void* user_stream, Stream** out) {
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            g_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " — dmrgx has no CPU path";
+            return 100;
+        }
+        CUDA_OK(cudaSetDevice(device));
+        Stream* st = new Stream();
+        st->device = device;
+        if (user_stream) { st->s = (cudaStream_t)user_stream; st->own = false; }
+        else { CUDA_OK(cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking)); st->own = true; }
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        st->num_sms = prop.multiProcessorCount;
+        cudaMemPool_t pool;
+        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long thr = ~0ULL;
+        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        CUDA_OK(cudaMalloc(&st->partials, sizeof(double) * RED_BLOCKS * RED_MAXVEC));
+        CUDA_OK(cudaMalloc(&st->info, sizeof(int) * 4));
+        if (cusolverDnCreate(&st->solver) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
+        cusolverDnSetStream(st->solver, st->s);
+        *out = st;
+        return 0;
+    } catch (const std::exception&) { return 100; }
+}
+
+void destroy(Stream* st) {
+    if (!st) return;
+    cudaSetDevice(st->device);
+    cudaStreamSynchronize(st->s);
+    if (st->solver) cusolverDnDestroy(st->solver);
+    if (st->solver_work) cudaFree(st->solver_work);
+    cudaFree(st->partials);
+    cudaFree(st->info);
+    if (st->own) cudaStreamDestroy(st->s);
+    delete st;
+}
+int device_of(Stream* st) { return st->device; }
+void* raw_stream(Stream* st) { return (void*)st->s; }
+
+void* malloc_bytes(Stream* st, size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 8;
+    CUDA_OK(cudaMallocAsync(&p, bytes, st->s));
+    return p;
+}
+void free_bytes(Stream* st, void* p) { if (p) cudaFreeAsync(p, st->s); }
+void* malloc_pinned(size_t bytes) { void* p = nullptr; CUDA_OK(cudaMallocHost(&p, bytes ? bytes : 8)); return p; }
+void free_pinned(void* p) { if (p) cudaFreeHost(p); }
+void h2d(Stream* st, void* dst, const void* src, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st->s)); }
+void d2h(Stream* st, void* dst, const void* src, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st->s)); }
+void d2d(Stream* st, void* dst, const void* src, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st->s)); }
+void memset0(Stream* st, void* dst, size_t bytes) { if (bytes) CUDA_OK(cudaMemsetAsync(dst, 0, bytes, st->s)); }
+void sync(Stream* st) { CUDA_OK(cudaStreamSynchronize(st->s)); }
+
+#define LAUNCH_CHECK() do { ++g_launches; CUDA_OK(cudaGetLastError()); } while (0)
+
+/* ================================================================================================
+ *  chain_kernel
+ * ============================================================================================== */
+constexpr int BM = 64, BN = 64, BK = 16, NTHREADS = 128;
+constexpr int S_MK = BK + 4;  /* [m][k] layout row stride (20 ≡ 4 mod 16) */
+constexpr int S_KM = BM + 4;  /* [k][m] layout row stride (68 ≡ 4 mod 16) */
+constexpr int SMEM_TILE = (BM * S_MK > BK * S_KM) ? BM * S_MK : BK * S_KM; /* 1280 doubles */
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+/* stage one K-chunk of both operands into shared memory */
+__device__ __forceinline__ void load_chunk(double* As, double* Bs, const double* __restrict__ Ab, const double* __restrict__ Bb,
+                                           long long lda_m, long long lda_k, long long ldb_n, long long ldb_k, int tm, int tn, int k0,
+                                           int K, bool a_mk, bool b_nk, int tid) {
+    if (a_mk) { /* contiguous along k: As[m][k] */
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / NTHREADS; ++i) {
+            int idx = tid + i * NTHREADS;
+            int m = idx / BK, k = idx % BK;
+            bool v = (m < tm) && (k0 + k < K);
+            const double* src = v ? (Ab + (long long)m * lda_m + (long long)(k0 + k) * lda_k) : Ab;
+            cp_async8(As + m * S_MK + k, src, v);
+        }
+    } else { /* contiguous along m: As[k][m] */
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / NTHREADS; ++i) {
+            int idx = tid + i * NTHREADS;
+            int k = idx / BM, m = idx % BM;
+            bool v = (m < tm) && (k0 + k < K);
+            const double* src = v ? (Ab + (long long)m * lda_m + (long long)(k0 + k) * lda_k) : Ab;
+            cp_async8(As + k * S_KM + m, src, v);
+        }
+    }
+    if (b_nk) { /* contiguous along k: Bs[n][k] */
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / NTHREADS; ++i) {
+            int idx = tid + i * NTHREADS;
+            int n = idx / BK, k = idx % BK;
+            bool v = (n < tn) && (k0 + k < K);
+            const double* src = v ? (Bb + (long long)n * ldb_n + (long long)(k0 + k) * ldb_k) : Bb;
+            cp_async8(Bs + n * S_MK + k, src, v);
+        }
+    } else { /* contiguous along n: Bs[k][n] */
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / NTHREADS; ++i) {
+            int idx = tid + i * NTHREADS;
+            int k = idx / BN, n = idx % BN;
+            bool v = (n < tn) && (k0 + k < K);
+            const double* src = v ? (Bb + (long long)n * ldb_n + (long long)(k0 + k) * ldb_k) : Bb;
+            cp_async8(Bs + k * S_KM + n, src, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __restrict__ items, const Segment* __restrict__ segs,
+                                                         const double* __restrict__ xbase, double* __restrict__ ybase) {
+    __shared__ double As[2][SMEM_TILE];
+    __shared__ double Bs[2][SMEM_TILE];
+    WorkItem it = items[blockIdx.x];
+    if (it.c_in_y) it.C = (double*)((char*)ybase + (size_t)it.C);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, t = lane & 3;
+    const int tm = it.tm, tn = it.tn;
+    /* number of valid 8-row / 8-col fragments of this warp (warp-uniform) */
+    int nmi = (tm - wm * 32 + 7) / 8; nmi = nmi < 0 ? 0 : (nmi > 4 ? 4 : nmi);
+    int nni = (tn - wn * 32 + 7) / 8; nni = nni < 0 ? 0 : (nni > 4 ? 4 : nni);
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+    for (int s = it.seg_begin; s < it.seg_end; ++s) {
+        Segment sg = segs[s];
+        if (sg.flags & SEGF_A_X) sg.A = (const double*)((const char*)xbase + (size_t)sg.A);
+        if (sg.flags & SEGF_B_X) sg.B = (const double*)((const char*)xbase + (size_t)sg.B);
+        if (sg.type == SEG_GEMM) {
+            const double* Ab = sg.A + (long long)it.m0 * sg.lda_m;
+            const double* Bb = sg.B + (long long)it.n0 * sg.ldb_n;
+            const bool a_mk = (sg.lda_k == 1) || (sg.lda_m != 1);
+            const bool b_nk = (sg.ldb_k == 1) || (sg.ldb_n != 1);
+            const int K = sg.K;
+            const int nchunks = (K + BK - 1) / BK;
+            const double coef = sg.coef;
+            const int a_sm = a_mk ? S_MK : 1, a_sk = a_mk ? 1 : S_KM;
+            const int b_sn = b_nk ? S_MK : 1, b_sk = b_nk ? 1 : S_KM;
+            __syncthreads(); /* previous segment's readers are done with both stages */
+            load_chunk(As[0], Bs[0], Ab, Bb, sg.lda_m, sg.lda_k, sg.ldb_n, sg.ldb_k, tm, tn, 0, K, a_mk, b_nk, tid);
+            cp_async_commit();
+            for (int c = 0; c < nchunks; ++c) {
+                const int cur = c & 1;
+                if (c + 1 < nchunks) {
+                    load_chunk(As[cur ^ 1], Bs[cur ^ 1], Ab, Bb, sg.lda_m, sg.lda_k, sg.ldb_n, sg.ldb_k, tm, tn, (c + 1) * BK, K, a_mk,
+                               b_nk, tid);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                const double* as = As[cur] + (wm * 32 + g) * a_sm + t * a_sk;
+                const double* bs = Bs[cur] + (wn * 32 + g) * b_sn + t * b_sk;
+#pragma unroll
+                for (int kk = 0; kk < BK / 4; ++kk) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = (mi < nmi) ? as[mi * 8 * a_sm + kk * 4 * a_sk] * coef : 0.0;
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) b[ni] = (ni < nni) ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni)
+                            if (mi < nmi && ni < nni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+                __syncthreads();
+            }
+        } else {
+            /* slow-path segments: each thread updates the accumulator elements it owns */
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = wm * 32 + mi * 8 + g;
+                if (row >= tm) continue;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = wn * 32 + ni * 8 + 2 * t + h;
+                        if (col >= tn) continue;
+                        const long long gm = it.m0 + row, gn = it.n0 + col;
+                        double v = 0.0;
+                        if (sg.type == SEG_AXPY) {
+                            v = sg.A[gm * sg.lda_m + gn * sg.lda_k];
+                        } else if (sg.type == SEG_DIAG) {
+                            v = (gm + sg.d == gn) ? 1.0 : 0.0;
+                        } else if (sg.type == SEG_CSRA) {
+                            const int r = sg.row0 + (int)gm;
+                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
+                                v += sg.B[e] * sg.A[(long long)sg.colidx[e] * sg.ldb_k + gn * sg.ldb_n];
+                        } else if (sg.type == SEG_CSRB) {
+                            const int r = sg.row0 + (int)gn;
+                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
+                                v += sg.B[e] * sg.A[gm * sg.lda_m + (long long)sg.colidx[e] * sg.lda_k];
+                        } else if (sg.type == SEG_CSRADD) {
+                            const int r = sg.row0 + (int)gm;
+                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
+                                if (sg.colidx[e] == (int)gn + sg.d) v += sg.B[e];
+                        }
+                        acc[mi][ni][h] += sg.coef * v;
+                    }
+                }
+            }
+        }
+    }
+    /* epilogue: each element written exactly once */
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int row = wm * 32 + mi * 8 + g;
+        if (row >= tm) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = wn * 32 + ni * 8 + 2 * t + h;
+                if (col >= tn) continue;
+                double* p = it.C + (long long)row * it.ldc + col;
+                if (it.mode == 0) *p = acc[mi][ni][h];
+                else atomicAdd(p, acc[mi][ni][h]);
+            }
+        }
+    }
+}
+
+void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y) {
+    if (nitems <= 0) return;
+    chain_kernel<<<nitems, NTHREADS, 0, st->s>>>(d_items, d_segs, x, y);
+    LAUNCH_CHECK();
+}
+
+/* ================================================================================================
+ *  Lanczos vector kernels — HBM-bound streaming kernels, 16-byte vector loads where aligned,
+ *  warp-shuffle + shared reductions, deterministic two-stage sums (no atomics).
+ * ============================================================================================== */
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void fill_random_kernel(double* x, long long n, unsigned long long seed) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = (double)(splitmix64(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL) >> 11) / 9007199254740992.0 - 0.5;
+}
+void fill_random(Stream* st, double* x, long long n, unsigned long long seed) {
+    int blocks = (int)std::min<long long>((n + 255) / 256, RED_BLOCKS);
+    fill_random_kernel<<<blocks, 256, 0, st->s>>>(x, n, seed);
+    LAUNCH_CHECK();
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) multidot_kernel(const double* __restrict__ V, long long ldv, int nvec, const double* __restrict__ w,
+                                                       long long n, double* __restrict__ partials) {
+    double s[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s[i] = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const double wq = w[q];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < nvec) s[i] += V[i * ldv + q] * wq;
+    }
+    __shared__ double sh[NV][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double v = warp_sum(s[i]);
+        if (lane == 0) sh[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += sh[threadIdx.x][k];
+        partials[(long long)blockIdx.x * NV + threadIdx.x] = v;
+    }
+}
+template <int NV>
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nvec, double* __restrict__ out) {
+    const int i = blockIdx.x; /* one block (32 threads) per output */
+    if (i >= nvec) return;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) v += partials[(long long)b * NV + i];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[i] = v;
+}
+
+void multidot(Stream* st, const double* V, long long ldv, int nvec, const double* w, long long n, double* d_out) {
+    constexpr int NV = 8;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    for (int v0 = 0; v0 < nvec; v0 += NV) {
+        const int nv = std::min(NV, nvec - v0);
+        multidot_kernel<NV><<<blocks, 256, 0, st->s>>>(V + (long long)v0 * ldv, ldv, nv, w, n, st->partials);
+        LAUNCH_CHECK();
+        reduce_partials_kernel<NV><<<nv, 32, 0, st->s>>>(st->partials, blocks, nv, d_out + v0);
+        LAUNCH_CHECK();
+    }
+}
+void dot(Stream* st, const double* x, const double* y, long long n, double* d_out) { multidot(st, x, n, 1, y, n, d_out); }
+
+template <int NV>
+__global__ void __launch_bounds__(256) multiaxpy_kernel(const double* __restrict__ V, long long ldv, int nvec, const double* __restrict__ coef,
+                                                        double* __restrict__ w, long long n) {
+    __shared__ double c[NV];
+    if (threadIdx.x < NV) c[threadIdx.x] = (threadIdx.x < nvec) ? coef[threadIdx.x] : 0.0;
+    __syncthreads();
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        double acc = w[q];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < nvec) acc -= c[i] * V[i * ldv + q];
+        w[q] = acc;
+    }
+}
+void multiaxpy(Stream* st, const double* V, long long ldv, int nvec, const double* d_coef, double* w, long long n, double* d_dots2,
+               double* d_nrm2) {
+    constexpr int NV = 8;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    for (int v0 = 0; v0 < nvec; v0 += NV) {
+        const int nv = std::min(NV, nvec - v0);
+        multiaxpy_kernel<NV><<<blocks, 256, 0, st->s>>>(V + (long long)v0 * ldv, ldv, nv, d_coef + v0, w, n);
+        LAUNCH_CHECK();
+    }
+    if (d_dots2) multidot(st, V, ldv, nvec, w, n, d_dots2);
+    if (d_nrm2) dot(st, w, w, n, d_nrm2);
+}
+
+__global__ void scale_inv_norm_kernel(const double* __restrict__ w, const double* __restrict__ nrm2, double* __restrict__ v, long long n) {
+    const double inv = 1.0 / sqrt(*nrm2);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) v[q] = w[q] * inv;
+}
+void scale_inv_norm(Stream* st, const double* w, const double* d_nrm2, double* v, long long n) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    scale_inv_norm_kernel<<<blocks, 256, 0, st->s>>>(w, d_nrm2, v, n);
+    LAUNCH_CHECK();
+}
+
+constexpr int RITZ_MAX = 40;
+__global__ void __launch_bounds__(256) ritz_rotate_kernel(double* __restrict__ V, long long ldv, long long n, int ncv, const double* __restrict__ S,
+                                                          int kk) {
+    extern __shared__ double sS[]; /* ncv*kk */
+    for (int i = threadIdx.x; i < ncv * kk; i += blockDim.x) sS[i] = S[i];
+    __syncthreads();
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        double v[RITZ_MAX];
+#pragma unroll 8
+        for (int i = 0; i < RITZ_MAX; ++i)
+            if (i < ncv) v[i] = V[i * ldv + q];
+        for (int a = 0; a < kk; ++a) {
+            double o = 0.0;
+            for (int i = 0; i < ncv; ++i) o += sS[i * kk + a] * v[i];
+            V[a * ldv + q] = o;
+        }
+    }
+}
+void ritz_rotate(Stream* st, double* V, long long ldv, long long n, int ncv, const double* d_S, int kk) {
+    if (ncv > RITZ_MAX) throw std::runtime_error("ritz_rotate: ncv too large");
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    ritz_rotate_kernel<<<blocks, 256, sizeof(double) * ncv * kk, st->s>>>(V, ldv, n, ncv, d_S, kk);
+    LAUNCH_CHECK();
+}
+
+__global__ void scal_kernel(double* x, long long n, double a) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) x[q] *= a;
+}
+void scal(Stream* st, double* x, long long n, double a) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    scal_kernel<<<blocks, 256, 0, st->s>>>(x, n, a);
+    LAUNCH_CHECK();
+}
+
+__global__ void filter_small_kernel(double* x, long long n, double tol) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        if (fabs(x[q]) < tol) x[q] = 0.0;
+}
+void filter_small(Stream* st, double* x, long long n, double tol) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    filter_small_kernel<<<blocks, 256, 0, st->s>>>(x, n, tol);
+    LAUNCH_CHECK();
+}
+
+__global__ void axpby_out_kernel(const double* a, const double* b, double alpha, double* out, long long n) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        out[q] = (a ? a[q] : 0.0) + alpha * b[q];
+}
+void axpby_out(Stream* st, const double* a, const double* b, double alpha, double* out, long long n) {
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+    axpby_out_kernel<<<blocks, 256, 0, st->s>>>(a, b, alpha, out, n);
+    LAUNCH_CHECK();
+}
+
+__global__ void gather_rows_reversed_kernel(const double* __restrict__ src, int n, int m, double* __restrict__ dst) {
+    const long long total = (long long)m * n;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(q / n), i = (int)(q % n);
+        dst[q] = src[(long long)(n - 1 - k) * n + i];
+    }
+}
+void gather_rows_reversed(Stream* st, const double* src, int n, int m, double* dst) {
+    if (m <= 0) return;
+    const long long total = (long long)m * n;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, RED_BLOCKS));
+    gather_rows_reversed_kernel<<<blocks, 256, 0, st->s>>>(src, n, m, dst);
+    LAUNCH_CHECK();
+}
+
+/* ================================================================================================
+ *  Dense symmetric eigendecomposition of one ρ block: cuSOLVER syevd (the reference calls LAPACK
+ *  through EPSLAPACK at include/DMRGBlockContainer.hpp:1976-1982 — a library call on both sides).
+ *  Column-major eigenvectors of a symmetric matrix == row-major rows, which is RotMatT's layout.
+ * ============================================================================================== */
+int syevd(Stream* st, int n, double* d_A, double* d_w) {
+    if (n <= 0) return 0;
+    int lwork = 0;
+    if (cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, d_A, n, d_w, &lwork) !=
+        CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnDsyevd_bufferSize failed"; return 102; }
+    const size_t need = sizeof(double) * (size_t)lwork;
+    if (need > st->solver_work_bytes) {
+        CUDA_OK(cudaStreamSynchronize(st->s));
+        if (st->solver_work) CUDA_OK(cudaFree(st->solver_work));
+        CUDA_OK(cudaMalloc(&st->solver_work, need));
+        st->solver_work_bytes = need;
+    }
+    cusolverStatus_t cs = cusolverDnDsyevd(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, d_A, n, d_w,
+                                           (double*)st->solver_work, lwork, st->info);
+    ++g_launches;
+    if (cs != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnDsyevd failed"; return 103; }
+    int info = 0;
+    CUDA_OK(cudaMemcpyAsync(&info, st->info, sizeof(int), cudaMemcpyDeviceToHost, st->s));
+    CUDA_OK(cudaStreamSynchronize(st->s));
+    if (info != 0) { g_err = "cusolverDnDsyevd: info != 0"; return 104; }
+    return 0;
+}
+
+}  // namespace dev

@@ -1,0 +1,135 @@
+/*  eigs.cpp — device-resident thick-restart Lanczos replacing the SLEPc call site
+ *  include/DMRGBlockContainer.hpp:1484-1500 (EPS_HEP, EPS_SMALLEST_REAL, nev = 1, Krylov-Schur).
+ *
+ *  The basis (ncv+1 vectors of length D), the work vector and every inner product live in HBM; per
+ *  Lanczos step the host sees ncv+2 doubles (the orthogonalisation coefficients and the residual
+ *  norm).  Same stopping rule as SLEPc's default: ||r|| <= tol·|theta|, tested at every restart;
+ *  same knobs (-H_eps_tol, -H_eps_ncv, -H_eps_max_it).
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+
+namespace dmrgx {
+
+/* tiny dense symmetric eigensolver for the (<= ncv × ncv) projected problem: cyclic Jacobi on the
+   host.  Ascending eigenvalues; column k of S (row-major n×n) is eigenvector k. */
+static void small_sym_eig(int n, std::vector<double> A, std::vector<double>& w, std::vector<double>& S) {
+    S.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) S[(size_t)i * n + i] = 1.0;
+    auto a = [&](int i, int j) -> double& { return A[(size_t)i * n + j]; };
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < n; ++i) { diag += a(i, i) * a(i, i); for (int j = i + 1; j < n; ++j) off += a(i, j) * a(i, j); }
+        if (off == 0.0 || off <= 1e-34 * (diag + off)) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                if (a(p, q) == 0.0) continue;
+                const double theta = (a(q, q) - a(p, p)) / (2.0 * a(p, q));
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) { const double x = a(k, p), y = a(k, q); a(k, p) = c * x - s * y; a(k, q) = s * x + c * y; }
+                for (int k = 0; k < n; ++k) { const double x = a(p, k), y = a(q, k); a(p, k) = c * x - s * y; a(q, k) = s * x + c * y; }
+                for (int k = 0; k < n; ++k) { const double x = S[(size_t)k * n + p], y = S[(size_t)k * n + q]; S[(size_t)k * n + p] = c * x - s * y; S[(size_t)k * n + q] = s * x + c * y; }
+            }
+    }
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; ++i) ord[i] = i;
+    std::vector<double> d(n);
+    for (int i = 0; i < n; ++i) d[i] = a(i, i);
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return d[x] < d[y]; });
+    std::vector<double> S2((size_t)n * n);
+    w.resize(n);
+    for (int k = 0; k < n; ++k) { w[k] = d[ord[k]]; for (int i = 0; i < n; ++i) S2[(size_t)i * n + k] = S[(size_t)i * n + ord[k]]; }
+    S.swap(S2);
+}
+
+double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* stats_out) {
+    Ctx* ctx = H->ctx;
+    dev::Stream* st = ctx->st;
+    const long long N = H->n;
+    EigsStats stats;
+    if (N <= 0) throw Err(ERR_GENERIC, "empty superblock");
+    const int ld = (int)std::max<long long>(1, std::min<long long>(opts.ncv < 2 ? 2 : opts.ncv, N));
+    /* SLEPc default max_it = max(100, 2N/ncv) restarts */
+    const long long max_it = opts.max_it > 0 ? opts.max_it : std::max<long long>(100, 2 * N / ld);
+    BufRef basis = std::make_shared<DevBuf>(ctx, (size_t)(ld + 1) * N * 8);
+    BufRef wbuf = std::make_shared<DevBuf>(ctx, (size_t)N * 8);
+    BufRef scal = std::make_shared<DevBuf>(ctx, (size_t)(2 * (ld + 2) + ld * ld) * 8);
+    double* V = basis->as<double>();
+    double* w = wbuf->as<double>();
+    double* d_h = scal->as<double>();            /* ld+1 coefficients, pass 1 */
+    double* d_h2 = d_h + (ld + 1);               /* pass 2 */
+    double* d_nrm2 = d_h2 + (ld + 1);
+    double* d_S = d_nrm2 + 2;
+    std::vector<double> hh(2 * (ld + 1) + 1);
+    std::vector<double> T((size_t)ld * ld, 0.0);
+
+    dev::fill_random(st, V, N, opts.seed);
+    dev::dot(st, V, V, N, d_nrm2);
+    dev::scale_inv_norm(st, V, d_nrm2, V, N);
+
+    int nc = ld, k = 0;
+    double theta = 0, resid = 0;
+    for (long long it = 0; it < max_it; ++it) {
+        double beta_last = 0;
+        bool invariant = false;
+        for (int j = k; j < nc; ++j) {
+            hshell_apply(H, V + (size_t)j * N, w);
+            stats.nmatvec++;
+            /* classical Gram-Schmidt against the whole basis, twice; coefficients never leave the device
+               except as the ncv+2 numbers the projected matrix needs */
+            dev::multidot(st, V, N, j + 1, w, N, d_h);
+            dev::multiaxpy(st, V, N, j + 1, d_h, w, N, d_h2, nullptr);
+            dev::multiaxpy(st, V, N, j + 1, d_h2, w, N, nullptr, d_nrm2);
+            dev::d2h(st, hh.data(), d_h, (size_t)(2 * (ld + 1) + 1) * 8);
+            dev::sync(st);
+            for (int i = 0; i <= j; ++i) {
+                const double c = hh[i] + hh[(ld + 1) + i];
+                T[(size_t)i * ld + j] = c;
+                T[(size_t)j * ld + i] = c;
+            }
+            const double b = std::sqrt(std::max(0.0, hh[2 * (ld + 1)]));
+            beta_last = b;
+            if (b < 1e-14) { nc = j + 1; invariant = true; break; }
+            dev::scale_inv_norm(st, w, d_nrm2, V + (size_t)(j + 1) * N, N);
+        }
+        std::vector<double> Tm((size_t)nc * nc), ev, S;
+        for (int i = 0; i < nc; ++i) for (int j = 0; j < nc; ++j) Tm[(size_t)i * nc + j] = T[(size_t)i * ld + j];
+        small_sym_eig(nc, Tm, ev, S); /* ascending: the wanted pair is column 0 */
+        theta = ev[0];
+        resid = invariant ? 0.0 : std::fabs(beta_last * S[(size_t)(nc - 1) * nc + 0]);
+        const bool conv = resid <= opts.tol * std::max(std::fabs(theta), 1e-300);
+        const bool last = conv || (it + 1 == max_it);
+        const int kk = last ? 1 : std::max(1, std::min(nc / 2, nc - 1));
+        std::vector<double> Skk((size_t)nc * kk);
+        for (int i = 0; i < nc; ++i) for (int a = 0; a < kk; ++a) Skk[(size_t)i * kk + a] = S[(size_t)i * nc + a];
+        dev::h2d(st, d_S, Skk.data(), Skk.size() * 8);
+        dev::sync(st);
+        if (!last) {
+            /* thick restart: V_0..V_kk-1 <- Ritz vectors, V_kk <- the residual direction */
+            std::fill(T.begin(), T.end(), 0.0);
+            for (int a = 0; a < kk; ++a) T[(size_t)a * ld + a] = ev[a];
+            /* the residual vector sits at index nc and must survive the in-place rotation of V_0..V_nc-1 */
+            dev::ritz_rotate(st, V, N, N, nc, d_S, kk);
+            if (kk != nc) dev::d2d(st, V + (size_t)kk * N, V + (size_t)nc * N, (size_t)N * 8);
+            k = kk;
+            stats.nrestart++;
+        } else {
+            dev::ritz_rotate(st, V, N, N, nc, d_S, 1);
+            stats.converged = conv ? 1 : 0;
+            break;
+        }
+    }
+    /* normalise the Ritz vector (it is unit up to round-off) and hand it over */
+    dev::dot(st, V, V, N, d_nrm2);
+    dev::scale_inv_norm(st, V, d_nrm2, d_psi, N);
+    dev::sync(st);
+    stats.resid = resid;
+    if (stats_out) *stats_out = stats;
+    return theta;
+}
+
+}  // namespace dmrgx

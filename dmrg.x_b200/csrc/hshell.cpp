@@ -1,0 +1,271 @@
+/*  hshell.cpp — KronBlocks_t bookkeeping and the matrix-free superblock Hamiltonian
+ *  (include/DMRGKron.hpp:117-480; src/DMRGKron.cpp:759-841, 891-989, 1706-1917).
+ *
+ *  The reference stores, per local row and per term, a 72-byte KronSumTermRow and pays nz_L·nz_R
+ *  multiply-adds per row per term.  Here the same operator,
+ *        Y_(IL,IR) += a · A[IL, IL+sA] · X_(IL+sA, IR+sB) · B[IR, IR+sB]ᵀ        
+ *  is planned once per superblock as two chain launches:
+ *     stage 1   V_g,p = A_g[IL, IL+sA] · X_q                    one panel per distinct left operator g
+ *     stage 2   Y_p   = Σ_g V_g,p · (Σ_j a_gj B_j[IR, IR+sB])ᵀ    all terms of a tile accumulated in registers
+ *  Terms are grouped by their left operator; right operators of a group that share a panel shape are
+ *  pre-summed at plan time.  Scaled-identity factors (H_L⊗1, 1⊗H_R, added-site operators) never
+ *  generate a product: they alias X or turn into an in-register AXPY.
+ */
+#include <algorithm>
+#include <cstring>
+#include <set>
+
+#include "common.h"
+#include "plan.h"
+
+namespace dmrgx {
+
+/* include/DMRGKron.hpp:124-213 */
+Kron* kron_create(const Block* L, const Block* R, const std::vector<double>& qn_sectors) {
+    if (!L || !R) throw std::runtime_error("Left/right input block not initialized.");
+    if (L->ctx != R->ctx) throw std::runtime_error("Left and right blocks must live in the same context.");
+    std::unique_ptr<Kron> k(new Kron());
+    k->ctx = L->ctx; k->L = L; k->R = R;
+    const Sectors &SL = L->sec, &SR = R->sec;
+    std::set<double> sel(qn_sectors.begin(), qn_sectors.end());
+    for (int il = 0; il < SL.nsec(); ++il)
+        for (int ir = 0; ir < SR.nsec(); ++ir) {
+            const double qn = SL.qn[il] + SR.qn[ir];
+            if (!qn_sectors.empty() && sel.find(qn) == sel.end()) continue; /* exact == on doubles, :165 */
+            k->pairs.push_back({qn, il, ir, SL.size[il] * SR.size[ir]});
+        }
+    if (qn_sectors.empty()) /* only the keep-everything case is sorted (:157) */
+        std::stable_sort(k->pairs.begin(), k->pairs.end(), [](const KronPair& a, const KronPair& b) { return a.qn > b.qn; });
+    k->off.assign(k->pairs.size() + 1, 0);
+    for (size_t p = 0; p < k->pairs.size(); ++p) {
+        k->off[p + 1] = k->off[p] + k->pairs[p].size;
+        k->map[{k->pairs[p].il, k->pairs[p].ir}] = (int)p;
+    }
+    return k.release();
+}
+
+HShell::~HShell() {
+    if (h_pinned) dev::free_pinned(h_pinned);
+}
+
+namespace {
+struct RightFactor { double coef; const Operator* B; };
+struct Group {
+    const Operator* A;      /* nullptr == identity */
+    int sA, sB;
+    std::vector<RightFactor> rights; /* B == nullptr == identity */
+};
+inline Tile full_eye(int off, int n) {
+    Tile t;
+    t.fmt = T_EYE; t.r0 = t.c0 = off; t.nr = t.nc = n; t.scale = 1.0;
+    return t;
+}
+inline bool contiguous_dense(const Tile& t) {
+    return t.fmt == T_DENSE && ((t.sc == 1 && t.sr == t.nc) || (t.sr == 1 && t.sc == t.nr));
+}
+}  // namespace
+
+static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, int nterms) {
+    Ctx* ctx = kron->ctx;
+    std::unique_ptr<HShell> H(new HShell());
+    H->ctx = ctx; H->kron = kron; H->n = kron->nstates(); H->nterms = nterms;
+    const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
+    const int np = (int)kron->pairs.size();
+    std::set<const void*> touched;
+    long long tile_bytes = 0;
+    auto touch = [&](const Tile& t) {
+        const void* key = t.fmt == T_DENSE ? (const void*)t.d : (t.fmt == T_CSR ? (const void*)t.val : nullptr);
+        if (key && touched.insert(key).second) tile_bytes += t.bytes();
+    };
+
+    /* ---- pass 1: size the V workspace ---- */
+    struct GP { long long voff; int q; };
+    std::vector<std::vector<GP>> gp(groups.size(), std::vector<GP>(np, GP{-1, -1}));
+    long long wtotal = 0;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const Group& G = groups[g];
+        for (int p = 0; p < np; ++p) {
+            const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
+            const int jl = il + G.sA, jr = ir + G.sB;
+            if (jl < 0 || jl >= SL.nsec() || jr < 0 || jr >= SR.nsec()) continue;
+            const int q = kron->find(jl, jr);
+            if (q < 0) continue;
+            gp[g][p].q = q;
+            bool needV = false;
+            if (G.A)
+                for (const Tile& t : G.A->tiles[il]) if (t.fmt != T_EYE) needV = true;
+            if (needV) { gp[g][p].voff = wtotal; wtotal += (long long)SL.size[il] * SR.size[jr]; }
+        }
+    }
+    H->work = std::make_shared<DevBuf>(ctx, std::max<long long>(1, wtotal) * 8);
+    double* W = H->work->as<double>();
+
+    /* ---- pre-summed right factors per (group, right row sector) ---- */
+    struct BTile { Tile t; double coef; };
+    std::vector<std::vector<std::vector<BTile>>> bt(groups.size(), std::vector<std::vector<BTile>>(SR.nsec()));
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const Group& G = groups[g];
+        for (int ir = 0; ir < SR.nsec(); ++ir) {
+            const int jr = ir + G.sB;
+            if (jr < 0 || jr >= SR.nsec()) continue;
+            std::vector<BTile> raw;
+            for (const RightFactor& rf : G.rights) {
+                if (!rf.B) { if (SR.size[ir] > 0) raw.push_back({full_eye(SR.off[ir], SR.size[ir]), rf.coef}); continue; }
+                for (const Tile& t : rf.B->tiles[ir]) raw.push_back({t, rf.coef});
+            }
+            std::vector<char> used(raw.size(), 0);
+            for (size_t a = 0; a < raw.size(); ++a) {
+                if (used[a]) continue;
+                used[a] = 1;
+                std::vector<size_t> same = {a};
+                if (contiguous_dense(raw[a].t))
+                    for (size_t b = a + 1; b < raw.size(); ++b)
+                        if (!used[b] && contiguous_dense(raw[b].t) && raw[b].t.r0 == raw[a].t.r0 && raw[b].t.c0 == raw[a].t.c0 &&
+                            raw[b].t.nr == raw[a].t.nr && raw[b].t.nc == raw[a].t.nc && raw[b].t.sr == raw[a].t.sr && raw[b].t.sc == raw[a].t.sc) {
+                            same.push_back(b); used[b] = 1;
+                        }
+                if (same.size() == 1) { bt[g][ir].push_back(raw[a]); touch(raw[a].t); continue; }
+                /* Σ_j a_j B_j materialised once (device axpy over the contiguous panels) */
+                const long long cnt = (long long)raw[a].t.nr * raw[a].t.nc;
+                BufRef sum = std::make_shared<DevBuf>(ctx, cnt * 8);
+                for (size_t k = 0; k < same.size(); ++k) {
+                    const BTile& s = raw[same[k]];
+                    dev::axpby_out(ctx->st, k == 0 ? nullptr : sum->as<double>(), s.t.d, s.coef, sum->as<double>(), cnt);
+                }
+                H->keep.push_back(sum);
+                BTile merged = raw[a];
+                merged.t.d = sum->as<double>(); merged.t.owner = sum; merged.coef = 1.0;
+                bt[g][ir].push_back(merged);
+                touch(merged.t);
+            }
+        }
+    }
+
+    /* ---- stage 1: V panels;  stage 2: Y panels ---- */
+    std::vector<std::vector<Contribution>> ycontrib(np);
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const Group& G = groups[g];
+        for (int p = 0; p < np; ++p) {
+            const int q = gp[g][p].q;
+            if (q < 0) continue;
+            const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
+            const int jl = il + G.sA, jr = ir + G.sB;
+            const int nLp = SL.size[il], nRq = SR.size[jr];
+            if (nLp == 0 || SR.size[ir] == 0 || nRq == 0 || SL.size[jl] == 0) continue;
+            const long long xq = kron->off[q];
+            std::vector<Tile> atiles;
+            if (G.A) atiles = G.A->tiles[il]; else atiles.push_back(full_eye(SL.off[il], nLp));
+            std::vector<Contribution> vcontrib;
+            for (const Tile& a : atiles) {
+                const int ra0 = a.r0 - SL.off[il], ca0 = a.c0 - SL.off[jl];
+                /* --- the left factor --- */
+                const double* vsrc; int vflags; double acoef = 1.0;
+                if (a.fmt == T_EYE) {
+                    vsrc = xoff(xq + (long long)ca0 * nRq); vflags = dev::SEGF_A_X; acoef = a.scale;
+                } else {
+                    touch(a);
+                    vsrc = W + gp[g][p].voff + (long long)ra0 * nRq; vflags = 0;
+                    Contribution c;
+                    c.r0 = ra0; c.c0 = 0; c.nr = a.nr; c.nc = nRq;
+                    if (a.fmt == T_DENSE) {
+                        c.seg = make_seg(dev::SEG_GEMM);
+                        c.seg.A = a.d; c.seg.lda_m = a.sr; c.seg.lda_k = a.sc; c.seg.K = a.nc;
+                        c.seg.B = xoff(xq + (long long)ca0 * nRq); c.seg.ldb_k = nRq; c.seg.ldb_n = 1; c.seg.flags = dev::SEGF_B_X;
+                    } else {
+                        c.seg = make_seg(dev::SEG_CSRA);
+                        c.seg.rowptr = a.rowptr; c.seg.colidx = a.col; c.seg.B = a.val;
+                        c.seg.A = xoff(xq + (long long)ca0 * nRq); c.seg.ldb_k = nRq; c.seg.ldb_n = 1; c.seg.flags = dev::SEGF_A_X;
+                    }
+                    vcontrib.push_back(c);
+                }
+                /* --- times every right factor of the group --- */
+                for (const BTile& bb : bt[g][ir]) {
+                    const Tile& b = bb.t;
+                    const int rb0 = b.r0 - SR.off[ir], cb0 = b.c0 - SR.off[jr];
+                    Contribution c;
+                    c.r0 = ra0; c.nr = a.nr; c.c0 = rb0; c.nc = b.nr;
+                    if (b.fmt == T_DENSE) {
+                        c.seg = make_seg(dev::SEG_GEMM);
+                        c.seg.A = vsrc + cb0; c.seg.lda_m = nRq; c.seg.lda_k = 1; c.seg.K = b.nc;
+                        c.seg.B = b.d; c.seg.ldb_n = b.sr; c.seg.ldb_k = b.sc;
+                        c.seg.coef = acoef * bb.coef;
+                    } else if (b.fmt == T_EYE) {
+                        c.seg = make_seg(dev::SEG_AXPY);
+                        c.seg.A = vsrc + cb0; c.seg.lda_m = nRq; c.seg.lda_k = 1;
+                        c.seg.coef = acoef * bb.coef * b.scale;
+                    } else {
+                        c.seg = make_seg(dev::SEG_CSRB);
+                        c.seg.A = vsrc + cb0; c.seg.lda_m = nRq; c.seg.lda_k = 1;
+                        c.seg.rowptr = b.rowptr; c.seg.colidx = b.col; c.seg.B = b.val;
+                        c.seg.coef = acoef * bb.coef;
+                    }
+                    c.seg.flags |= vflags;
+                    ycontrib[p].push_back(c);
+                }
+            }
+            if (!vcontrib.empty()) emit_cells(H->stage1, W + gp[g][p].voff, false, nRq, nLp, nRq, vcontrib, false);
+        }
+    }
+    for (int p = 0; p < np; ++p) {
+        const int nLp = SL.size[kron->pairs[p].il], nRp = SR.size[kron->pairs[p].ir];
+        emit_cells(H->stage2, yoff(kron->off[p]), true, nRp, nLp, nRp, ycontrib[p], true);
+    }
+    H->stage1.upload(ctx);
+    H->stage2.upload(ctx);
+    H->alg_bytes = 16LL * H->n + tile_bytes;
+    H->alg_flops = H->stage1.flops + H->stage2.flops;
+    return H.release();
+}
+
+/* src/DMRGKron.cpp:759-841 (classification, reflection) + :891-989 (term list = H_L⊗1, 1⊗H_R, LR terms) */
+HShell* hshell_create(const Kron* kron, const std::vector<Term>& terms) {
+    const Block *L = kron->L, *R = kron->R;
+    const int nsL = L->nsites, nsR = R->nsites, nsO = nsL + nsR;
+    long long maxsite = 0;
+    for (const Term& t : terms) maxsite = std::max({maxsite, t.Isite, t.Jsite});
+    if (maxsite >= nsO) throw Err(ERR_GENERIC, "Maximum site index from Terms has to be less than the total number of sites in the blocks.");
+    block_check(L);
+    block_check(R);
+    std::vector<Term> lr;
+    for (const Term& t : terms) {
+        if (t.Isite >= 0 && t.Isite < nsL && t.Jsite >= nsL && t.Jsite < nsO) {
+            if (t.a == 0.0) continue;
+            Term u = t;
+            u.Jsite = nsO - 1 - t.Jsite;
+            lr.push_back(u);
+        } else if (t.Isite >= 0 && t.Isite < nsL && t.Jsite >= 0 && t.Jsite < nsL) {
+        } else if (t.Isite >= nsL && t.Isite < nsO && t.Jsite >= nsL && t.Jsite < nsO) {
+        } else throw Err(ERR_GENERIC, "Invalid term.");
+    }
+    std::vector<Group> groups;
+    groups.push_back({&L->H, 0, 0, {{1.0, nullptr}}});  /* H_L ⊗ 1 */
+    groups.push_back({nullptr, 0, 0, {{1.0, &R->H}}});  /* 1 ⊗ H_R */
+    std::map<std::tuple<int, long long, int>, size_t> gidx;
+    for (const Term& t : lr) {
+        if (t.Iop < OP_SM || t.Iop > OP_SP || t.Jop < OP_SM || t.Jop > OP_SP) throw Err(ERR_ARG_WRONG, "Incorrect operator type.");
+        const Operator* A = L->op(t.Iop, (int)t.Isite);
+        const Operator* B = R->op(t.Jop, (int)t.Jsite);
+        auto key = std::make_tuple(t.Iop, t.Isite, t.Jop);
+        auto f = gidx.find(key);
+        if (f == gidx.end()) { gidx[key] = groups.size(); groups.push_back({A, t.Iop, t.Jop, {}}); f = gidx.find(key); }
+        groups[f->second].rights.push_back({t.a, B});
+    }
+    return build_shell(kron, groups, 2 + (int)lr.size());
+}
+
+/* KronConstruct, include/DMRGKron.hpp:309 / src/DMRGKron.cpp:618-694: one term 1.0 · A ⊗ B (correlators) */
+HShell* hshell_create_single(const Kron* kron, int opl, int il, int opr, int ir) {
+    const Operator* A = opl == OP_EYE ? nullptr : kron->L->op(opl, il);
+    const Operator* B = opr == OP_EYE ? nullptr : kron->R->op(opr, ir);
+    std::vector<Group> groups;
+    groups.push_back({A, opl == OP_EYE ? 0 : opl, opr == OP_EYE ? 0 : opr, {{1.0, B}}});
+    return build_shell(kron, groups, 1);
+}
+
+/* MatMult_KronSumShell, src/DMRGKron.cpp:1827-1869 */
+void hshell_apply(HShell* H, const double* d_x, double* d_y) {
+    H->stage1.run(H->ctx, d_x, nullptr);
+    H->stage2.run(H->ctx, d_x, d_y);
+}
+
+}  // namespace dmrgx

@@ -1,0 +1,104 @@
+/*  plan.cpp — turns "output panel + list of rectangular contributions" into the flat work-item /
+ *  segment lists the chain kernel consumes (dev.h).  Every output element is produced by exactly one
+ *  work item, so there is no zero-fill pass and no atomics: the panel is cut along the edges of all
+ *  contributing rectangles into cells, every cell is covered by a fixed set of contributions, and each
+ *  cell is tiled with (almost) equal tiles of at most dev::TILE × dev::TILE.
+ */
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+#include "plan.h"
+
+namespace dmrgx {
+
+void Plan::upload(Ctx* ctx) {
+    if (items.empty()) return;
+    /* heaviest tiles first: the hardware dispatches CTAs in index order, so this is LPT scheduling */
+    std::vector<double> cost(items.size());
+    for (size_t i = 0; i < items.size(); ++i) {
+        double c = 0;
+        for (int s = items[i].seg_begin; s < items[i].seg_end; ++s) c += segs[s].type == dev::SEG_GEMM ? (double)segs[s].K : 1.0;
+        cost[i] = c * items[i].tm * items[i].tn + 64.0;
+    }
+    std::vector<size_t> ord(items.size());
+    for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+    std::vector<dev::WorkItem> sorted(items.size());
+    for (size_t i = 0; i < ord.size(); ++i) sorted[i] = items[ord[i]];
+    items.swap(sorted);
+    d_items = std::make_shared<DevBuf>(ctx, items.size() * sizeof(dev::WorkItem));
+    d_segs = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, segs.size()) * sizeof(dev::Segment));
+    dev::h2d(ctx->st, d_items->p, items.data(), items.size() * sizeof(dev::WorkItem));
+    dev::h2d(ctx->st, d_segs->p, segs.data(), segs.size() * sizeof(dev::Segment));
+    dev::sync(ctx->st); /* the host vectors may be reallocated by the caller afterwards */
+}
+
+void Plan::run(Ctx* ctx, const double* x, double* y) const {
+    if (items.empty()) return;
+    dev::run_chain(ctx->st, d_items->as<dev::WorkItem>(), (int)items.size(), d_segs->as<dev::Segment>(), x, y);
+}
+
+static inline const double* padd(const double* p, long long elems) { return p + elems; }
+
+void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Ncols, const std::vector<Contribution>& contribs,
+                bool cover_all) {
+    if (R <= 0 || Ncols <= 0) return;
+    std::vector<int> rc = {0, R}, cc = {0, Ncols};
+    for (const Contribution& c : contribs) {
+        if (c.nr <= 0 || c.nc <= 0) continue;
+        if (c.r0 < 0 || c.c0 < 0 || c.r0 + c.nr > R || c.c0 + c.nc > Ncols) throw Err(ERR_GENERIC, "emit_cells: contribution outside the panel");
+        rc.push_back(c.r0); rc.push_back(c.r0 + c.nr);
+        cc.push_back(c.c0); cc.push_back(c.c0 + c.nc);
+    }
+    std::sort(rc.begin(), rc.end()); rc.erase(std::unique(rc.begin(), rc.end()), rc.end());
+    std::sort(cc.begin(), cc.end()); cc.erase(std::unique(cc.begin(), cc.end()), cc.end());
+    for (size_t ri = 0; ri + 1 < rc.size(); ++ri) {
+        const int r0 = rc[ri], r1 = rc[ri + 1];
+        for (size_t ci = 0; ci + 1 < cc.size(); ++ci) {
+            const int c0 = cc[ci], c1 = cc[ci + 1];
+            const int seg_begin = (int)plan.segs.size();
+            double kflops = 0;
+            for (const Contribution& c : contribs) {
+                if (c.nr <= 0 || c.nc <= 0) continue;
+                if (!(c.r0 <= r0 && r1 <= c.r0 + c.nr && c.c0 <= c0 && c1 <= c.c0 + c.nc)) continue;
+                dev::Segment s = c.seg;
+                const long long dr = r0 - c.r0, dc = c0 - c.c0;
+                switch (s.type) {
+                    case dev::SEG_GEMM: s.A = padd(s.A, dr * s.lda_m); s.B = padd(s.B, dc * s.ldb_n); kflops += 2.0 * s.K; break;
+                    case dev::SEG_AXPY: s.A = padd(s.A, dr * s.lda_m + dc * s.lda_k); break;
+                    case dev::SEG_DIAG: s.d = (int)(s.d + dr - dc); break;
+                    case dev::SEG_CSRA: s.row0 += (int)dr; s.A = padd(s.A, dc * s.ldb_n); break;
+                    case dev::SEG_CSRB: s.row0 += (int)dc; s.A = padd(s.A, dr * s.lda_m); break;
+                    case dev::SEG_CSRADD: s.row0 += (int)dr; s.d = (int)(s.d + dc); break;
+                    default: throw Err(ERR_GENERIC, "emit_cells: bad segment type");
+                }
+                plan.segs.push_back(s);
+            }
+            const int seg_end = (int)plan.segs.size();
+            if (seg_end == seg_begin && !cover_all) continue;
+            const int M = r1 - r0, N = c1 - c0;
+            const int nmt = (M + dev::TILE - 1) / dev::TILE, nnt = (N + dev::TILE - 1) / dev::TILE;
+            /* balanced extents, multiples of 8 (the DMMA fragment edge) */
+            const int tm = std::min(dev::TILE, ((M + nmt - 1) / nmt + 7) / 8 * 8);
+            const int tn = std::min(dev::TILE, ((N + nnt - 1) / nnt + 7) / 8 * 8);
+            for (int m0 = 0; m0 < M; m0 += tm)
+                for (int n0 = 0; n0 < N; n0 += tn) {
+                    dev::WorkItem it;
+                    std::memset(&it, 0, sizeof it);
+                    it.C = C + (long long)(r0 + m0) * ldc + (c0 + n0);
+                    it.ldc = ldc;
+                    it.m0 = m0; it.n0 = n0;
+                    it.tm = std::min(tm, M - m0);
+                    it.tn = std::min(tn, N - n0);
+                    it.seg_begin = seg_begin; it.seg_end = seg_end;
+                    it.mode = 0;
+                    it.c_in_y = c_in_y ? 1 : 0;
+                    plan.items.push_back(it);
+                }
+            plan.flops += kflops * (double)M * (double)N;
+        }
+    }
+}
+
+}  // namespace dmrgx

@@ -1,0 +1,140 @@
+/*  dmrgx.h — C ABI of the B200-native superblock-diagonalisation path of DMRG.x.
+ *
+ *  This is the drop-in boundary: each entry point replaces one piece of the reference's hot path and
+ *  cites it (paths relative to the reference tree).  A maintainer of the reference binds these from
+ *  KronBlocks_t / Block::SpinBase / DMRGBlockContainer (see INTEGRATION.md for the stubs).
+ *
+ *  Conventions
+ *    - every function returns an int status, 0 = success; non-zero values reuse the PETSc error codes
+ *      the reference returns on this path (63 PETSC_ERR_ARG_OUTOFRANGE, 62 PETSC_ERR_ARG_WRONG,
+ *      73 PETSC_ERR_ARG_WRONGSTATE, 64 PETSC_ERR_ARG_CORRUPT, 56 PETSC_ERR_SUP, 1 generic,
+ *      100+ = CUDA / no device).  dmrgx_last_error() gives the message.  No exception crosses the ABI.
+ *    - opaque handles; the library owns all device memory; the caller owns host buffers; every
+ *      *_create / *_upload has a matching *_destroy.  One driving host thread per context.
+ *    - index type is 64-bit (`dmrgx_int`), matching a 64-bit-PetscInt build; operator enum values are
+ *      the reference's Op_t (include/DMRGBlock.hpp:21-27) and double as the Sz sector shift.
+ *    - there is NO CPU path: dmrgx_ctx_create fails with 100 when no CUDA device is present.
+ */
+#ifndef DMRGX_H
+#define DMRGX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long long dmrgx_int;
+
+typedef struct dmrgx_ctx_s* dmrgx_ctx;
+typedef struct dmrgx_block_s* dmrgx_block;
+typedef struct dmrgx_kron_s* dmrgx_kron;
+typedef struct dmrgx_hshell_s* dmrgx_hshell;
+typedef struct dmrgx_xform_s* dmrgx_xform;
+
+/* include/DMRGBlock.hpp:21-27 (+ H, which the reference keeps as a separate Mat member) */
+enum { DMRGX_OP_SM = -1, DMRGX_OP_SZ = 0, DMRGX_OP_SP = 1, DMRGX_OP_EYE = 2, DMRGX_OP_H = 3 };
+
+const char* dmrgx_last_error(void);
+/* number of kernels this library has launched so far in this process */
+dmrgx_int dmrgx_launch_count(void);
+
+/* ---- context: one CUDA device + stream (replaces the MPI communicator of the reference objects) ---- */
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create a private one */
+int dmrgx_ctx_create(int device, void* stream, dmrgx_ctx* out);
+int dmrgx_ctx_destroy(dmrgx_ctx ctx);
+int dmrgx_ctx_sync(dmrgx_ctx ctx);
+/* fill fraction above which a sector-block panel is stored dense (default 0.125) */
+int dmrgx_ctx_set_dense_threshold(dmrgx_ctx ctx, double fill);
+
+/* ---- Block::SpinBase (include/DMRGBlock.hpp:79-434) ---- */
+/* Initialize(comm, nsites, qn_list, qn_size): include/DMRGBlock.hpp:243-250, src/DMRGBlock.cpp:173-196 */
+int dmrgx_block_create(dmrgx_ctx ctx, dmrgx_int nsites, dmrgx_int nsectors, const double* qn_list, const dmrgx_int* qn_size,
+                       dmrgx_block* out);
+/* Initialize(comm, 1, PETSC_DEFAULT): one site with the default spin operators, src/DMRGBlock.cpp:123-137, 1106-1225.
+   spin_twice: 1 = spin-1/2 (default), 2 = spin-1 (-spin option, src/DMRGBlock.cpp:54-94) */
+int dmrgx_block_single_site(dmrgx_ctx ctx, int spin_twice, dmrgx_block* out);
+/* Sz(i) / Sp(i) / H as CSR with global column indices (what MatGetRow / MatSeqAIJGetArray give).  op in
+   {DMRGX_OP_SZ, DMRGX_OP_SP, DMRGX_OP_H}; Sm is derived (CreateSm, src/DMRGBlock.cpp:623-636).  Entries
+   outside the operator's sector block fail with 63 like MatCheckOperatorBlocks (src/DMRGBlock.cpp:508-600). */
+int dmrgx_block_set_operator(dmrgx_block blk, int op, dmrgx_int isite, const dmrgx_int* rowptr, const dmrgx_int* colidx,
+                             const double* values);
+/* read an operator back as CSR: call with colidx == NULL to get nnz, then with buffers (rowptr: nstates+1) */
+int dmrgx_block_get_operator(dmrgx_block blk, int op, dmrgx_int isite, dmrgx_int* nnz, dmrgx_int* rowptr, dmrgx_int* colidx,
+                             double* values);
+int dmrgx_block_info(dmrgx_block blk, dmrgx_int* nsites, dmrgx_int* nstates, dmrgx_int* nsectors);
+/* Magnetization.List() / Sizes(): include/QuantumNumbers.hpp:84-98 */
+int dmrgx_block_sectors(dmrgx_block blk, double* qn_list, dmrgx_int* qn_size);
+/* CheckOperatorBlocks: src/DMRGBlock.cpp:603-620 */
+int dmrgx_block_check(dmrgx_block blk);
+int dmrgx_block_destroy(dmrgx_block blk);
+/* KronEye_Explicit(Left, AddSite, Terms, BlockOut): src/DMRGKron.cpp:459-615.  `site` must have one state per
+   sector (a single site, which is the only way the reference's DMRG loop calls it). */
+int dmrgx_block_enlarge(dmrgx_block left, dmrgx_block site, dmrgx_int nterms, const double* a, const int* iop, const dmrgx_int* isite,
+                        const int* jop, const dmrgx_int* jsite, dmrgx_block* out);
+
+/* ---- KronBlocks_t (include/DMRGKron.hpp:117-480) ---- */
+/* ctor :124-213; nqn == 0 keeps every sector (and sorts by descending QN), else only the listed ones */
+int dmrgx_kron_create(dmrgx_block left, dmrgx_block right, dmrgx_int nqn, const double* qn_sectors, dmrgx_kron* out);
+int dmrgx_kron_destroy(dmrgx_kron k);
+dmrgx_int dmrgx_kron_size(dmrgx_kron k);                                 /* size()       :216 */
+dmrgx_int dmrgx_kron_num_states(dmrgx_kron k);                           /* NumStates()  :297 */
+/* data(): QN, LeftIdx, RightIdx, Sizes (size() entries each) and Offsets (size()+1)  :219-262 */
+int dmrgx_kron_data(dmrgx_kron k, double* qn, dmrgx_int* left_idx, dmrgx_int* right_idx, dmrgx_int* sizes, dmrgx_int* offsets);
+dmrgx_int dmrgx_kron_map(dmrgx_kron k, dmrgx_int lidx, dmrgx_int ridx);      /* Map(l,r), -1 if absent      :283-294 */
+dmrgx_int dmrgx_kron_offsets_lr(dmrgx_kron k, dmrgx_int lidx, dmrgx_int ridx); /* Offsets(l,r), -1 if absent :272-276 */
+
+/* ---- the shell Hamiltonian ---- */
+/* KronSumConstruct(Terms, H) with do_shell: src/DMRGKron.cpp:759-841, 1871-1917.  Terms are the full list
+   Ham.H(nsites_total); intra-block terms are ignored and the right sites reflected exactly as :788-807. */
+int dmrgx_hshell_create(dmrgx_kron k, dmrgx_int nterms, const double* a, const int* iop, const dmrgx_int* isite, const int* jop,
+                        const dmrgx_int* jsite, dmrgx_hshell* out);
+/* KronConstruct(Mat_L, OpType_L, Mat_R, OpType_R, MatOut): include/DMRGKron.hpp:309 — one term 1.0·A⊗B; an op of
+   DMRGX_OP_EYE means identity on that side */
+int dmrgx_hshell_create_single(dmrgx_kron k, int op_left, dmrgx_int isite_left, int op_right, dmrgx_int isite_right, dmrgx_hshell* out);
+/* MatMult_KronSumShell(A, x, y): src/DMRGKron.cpp:1827-1869.  Device pointers, length NumStates(). */
+int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y);
+/* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, apply, D2H, synchronous */
+int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y);
+/* MatDestroy_KronSumShell: src/DMRGKron.cpp:1919-1942 */
+int dmrgx_hshell_destroy(dmrgx_hshell h);
+/* algorithmic bytes / flops of one apply and the number of shell terms */
+int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, double* alg_bytes, double* alg_flops,
+                       dmrgx_int* ntiles_stage1, dmrgx_int* ntiles_stage2);
+
+/* ---- ground state: EPSSolve + EPSGetEigenpair(0), include/DMRGBlockContainer.hpp:1484-1500 ---- */
+typedef struct {
+    double tol;               /* -H_eps_tol    (SLEPc default 1e-8)  */
+    dmrgx_int ncv;            /* -H_eps_ncv    (SLEPc default 16)    */
+    dmrgx_int max_it;         /* -H_eps_max_it (0: max(100, 2N/ncv)) */
+    unsigned long long seed;  /* start vector */
+} dmrgx_eigs_opts;
+typedef struct { dmrgx_int nmatvec, nrestart, converged; double resid; } dmrgx_eigs_stats;
+int dmrgx_eigs_smallest(dmrgx_hshell h, const dmrgx_eigs_opts* opts, double* e0, double* d_psi, dmrgx_eigs_stats* stats);
+
+/* ---- truncation: GetTruncation, include/DMRGBlockContainer.hpp:1656-1959 ---- */
+int dmrgx_truncate(dmrgx_kron k, const double* d_psi, dmrgx_int mstates, dmrgx_xform* left, dmrgx_xform* right);
+/* m = RotMatT rows, nstates = columns, nsectors of BT.QN, TruncErr, and the size of the grouped spectrum */
+int dmrgx_xform_info(dmrgx_xform x, dmrgx_int* m, dmrgx_int* nstates, dmrgx_int* nsectors, double* trunc_err, dmrgx_int* nspectrum);
+int dmrgx_xform_sectors(dmrgx_xform x, double* qn_list, dmrgx_int* qn_size);
+/* unsorted, grouped eigenvalues + their block index, as SaveEntanglementSpectra dumps them (:1790-1793) */
+int dmrgx_xform_spectrum(dmrgx_xform x, double* eigval, dmrgx_int* blk_idx);
+/* RotMatT as a dense m × nstates row-major host matrix (debug / parity) */
+int dmrgx_xform_rotmat(dmrgx_xform x, double* out);
+int dmrgx_xform_destroy(dmrgx_xform x);
+
+/* ---- rotation: SysBlockOut.Initialize(nsites, BT.QN) + RotateOperators(SysBlockEnl, RotMatT),
+        include/DMRGBlockContainer.hpp:1561-1563, src/DMRGBlock.cpp:677-823 ---- */
+int dmrgx_rotate(dmrgx_block enlarged, dmrgx_xform x, dmrgx_block* out);
+
+/* ---- correlator kernel: <psi| A⊗B |psi> = VecDot(psi, MatMult(H1, psi)), include/DMRGBlockContainer.hpp:2287-2296 ---- */
+int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value);
+
+/* ---- device vectors (the Vec objects of the callers) ---- */
+int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out);
+int dmrgx_vec_free(dmrgx_ctx ctx, double* d);
+int dmrgx_vec_set(dmrgx_ctx ctx, double* d_dst, const double* h_src, dmrgx_int n);
+int dmrgx_vec_get(dmrgx_ctx ctx, double* h_dst, const double* d_src, dmrgx_int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMRGX_H */
