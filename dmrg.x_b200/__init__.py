@@ -55,7 +55,7 @@ def lib():
             raise DmrgxError(100, "%s is missing: build it with __graft_entry__.build() (there is no CPU fallback)" % path)
         L = C.CDLL(path)
         L.dmrgx_last_error.restype = C.c_char_p
-        for n in ("dmrgx_launch_count", "dmrgx_kron_size", "dmrgx_kron_num_states", "dmrgx_kron_map", "dmrgx_kron_offsets_lr"):
+        for n in ("dmrgx_ham_terms", "dmrgx_launch_count", "dmrgx_kron_size", "dmrgx_kron_num_states", "dmrgx_kron_map", "dmrgx_kron_offsets_lr"):
             getattr(L, n).restype = LL
         _lib = L
     return _lib
@@ -89,6 +89,20 @@ def launch_count():
 def _terms_arrays(terms):
     return (_d([t[0] for t in terms]), _i([t[1] for t in terms]), _l([t[2] for t in terms]), _i([t[3] for t in terms]),
             _l([t[4] for t in terms]))
+
+
+def HamiltonianTerms(Lx, Ly, J1=1.0, Jz1=0.0, J2=1.0, Jz2=0.0, nsites=-1, bcx=0, bcy=1, heisenberg=None):
+    """Hamiltonians::J1J2XXZModel_SquareLattice::H(nsites) — src/Hamiltonians.cpp:73-122; defaults and the
+    -heisenberg override follow include/Hamiltonians.hpp:93-115, 240-265."""
+    if heisenberg is not None:
+        Jz1, J1, J2, Jz2 = heisenberg, 0.5, 0.0, 0.0
+    cap = 16 * max(Lx * Ly, 1) * 3 + 16
+    a = np.zeros(cap); iop = np.zeros(cap, np.int32); isite = np.zeros(cap, np.int64); jop = np.zeros(cap, np.int32)
+    jsite = np.zeros(cap, np.int64)
+    k = lib().dmrgx_ham_terms(LL(Lx), LL(Ly), C.c_double(J1), C.c_double(Jz1), C.c_double(J2), C.c_double(Jz2), int(bcx), int(bcy),
+                              LL(nsites), LL(cap), _p(a), _p(iop), _p(isite), _p(jop), _p(jsite))
+    assert k <= cap
+    return [(float(a[i]), int(iop[i]), int(isite[i]), int(jop[i]), int(jsite[i])) for i in range(k)]
 
 
 class Context:
@@ -292,6 +306,14 @@ class HShell:
         xp = x.ptr if isinstance(x, DeviceVector) else C.c_void_p(int(x))
         yp = y.ptr if isinstance(y, DeviceVector) else C.c_void_p(int(y))
         _chk(lib().dmrgx_hshell_apply(self.h, xp, yp))
+
+    def MatMult_stage(self, stage, x, y):
+        _chk(lib().dmrgx_hshell_apply_stage(self.h, int(stage), x.ptr, y.ptr))
+
+    def stage_flops(self):
+        a, b = C.c_double(), C.c_double()
+        _chk(lib().dmrgx_hshell_stage_flops(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def MatMult_host(self, x, y=None):
         """The PETSc-callback shape: host arrays in and out (H2D + kernels + D2H inside)."""

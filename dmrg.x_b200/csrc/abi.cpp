@@ -117,6 +117,18 @@ int dmrgx_hshell_create_single(dmrgx_kron k, int opl, dmrgx_int il, int opr, dmr
     return guard([&] { *out = (dmrgx_hshell)hshell_create_single(K(k), opl, (int)il, opr, (int)ir); });
 }
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y) { return guard([&] { hshell_apply(H(h), d_x, d_y); }); }
+int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y) {
+    return guard([&] {
+        HShell* s = H(h);
+        if (stage == 1) s->stage1.run(s->ctx, d_x, nullptr);
+        else if (stage == 2) s->stage2.run(s->ctx, d_x, d_y);
+        else throw Err(ERR_ARG_WRONG, "stage must be 1 or 2");
+    });
+}
+int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops1, double* flops2) {
+    *flops1 = H(h)->stage1.flops; *flops2 = H(h)->stage2.flops;
+    return 0;
+}
 int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
     return guard([&] {
         HShell* s = H(h);
@@ -216,6 +228,15 @@ int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value) {
         dev::d2h(ctx->st, value, d_out, 8);
         dev::sync(ctx->st);
     });
+}
+
+dmrgx_int dmrgx_ham_terms(dmrgx_int Lx, dmrgx_int Ly, double J1, double Jz1, double J2, double Jz2, int bcx, int bcy, dmrgx_int nsites,
+                          dmrgx_int maxterms, double* a, int* iop, dmrgx_int* isite, int* jop, dmrgx_int* jsite) {
+    std::vector<Term> t = ham_terms(Lx, Ly, J1, Jz1, J2, Jz2, bcx, bcy, nsites);
+    for (dmrgx_int i = 0; i < (dmrgx_int)t.size() && i < maxterms; ++i) {
+        a[i] = t[i].a; iop[i] = t[i].Iop; isite[i] = t[i].Isite; jop[i] = t[i].Jop; jsite[i] = t[i].Jsite;
+    }
+    return (dmrgx_int)t.size();
 }
 
 int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out) { return guard([&] { *d_out = (double*)dev::malloc_bytes(C(ctx)->st, (size_t)n * 8); }); }

@@ -162,6 +162,8 @@ Block* block_single_site(Ctx*, int spin_twice);
 Block* block_enlarge(const Block* L, const Block* site, const std::vector<Term>& terms);
 void block_check(const Block*);
 
+std::vector<Term> ham_terms(long long Lx, long long Ly, double J1, double Jz1, double J2, double Jz2, int bcx, int bcy, long long nsites);
+
 Kron* kron_create(const Block* L, const Block* R, const std::vector<double>& qn_sectors);
 
 HShell* hshell_create(const Kron*, const std::vector<Term>& terms);

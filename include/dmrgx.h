@@ -92,6 +92,9 @@ int dmrgx_hshell_create(dmrgx_kron k, dmrgx_int nterms, const double* a, const i
 int dmrgx_hshell_create_single(dmrgx_kron k, int op_left, dmrgx_int isite_left, int op_right, dmrgx_int isite_right, dmrgx_hshell* out);
 /* MatMult_KronSumShell(A, x, y): src/DMRGKron.cpp:1827-1869.  Device pointers, length NumStates(). */
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y);
+/* profiling aids: run only stage 1 (V = A·X panels) or stage 2 (Y = Σ V·Bᵀ) of an apply, and their useful flops */
+int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y);
+int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
 /* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, apply, D2H, synchronous */
 int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y);
 /* MatDestroy_KronSumShell: src/DMRGKron.cpp:1919-1942 */
@@ -127,6 +130,11 @@ int dmrgx_rotate(dmrgx_block enlarged, dmrgx_xform x, dmrgx_block* out);
 
 /* ---- correlator kernel: <psi| A⊗B |psi> = VecDot(psi, MatMult(H1, psi)), include/DMRGBlockContainer.hpp:2287-2296 ---- */
 int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value);
+
+/* ---- Hamiltonians::J1J2XXZModel_SquareLattice::H(nsites): src/Hamiltonians.cpp:73-122 (host only).
+        Returns the number of terms (fills at most maxterms); bc: 0 open, 1 periodic; nsites < 0 = full lattice. ---- */
+dmrgx_int dmrgx_ham_terms(dmrgx_int Lx, dmrgx_int Ly, double J1, double Jz1, double J2, double Jz2, int bcx, int bcy, dmrgx_int nsites,
+                          dmrgx_int maxterms, double* a, int* iop, dmrgx_int* isite, int* jop, dmrgx_int* jsite);
 
 /* ---- device vectors (the Vec objects of the callers) ---- */
 int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out);

@@ -491,7 +491,8 @@ struct KronBlocks_t {
     Int NumStates() const { return num_states; }
 
     void KronSumConstructExplicit(const Block& L, const Block& R, const std::vector<Term>& TermsLR, CSR& MatOut) const;
-    void KronSumConstruct(Block& L, Block& R, const std::vector<Term>& Terms, CSR* MatOutExplicit, KronSumShell* shell) const;
+    void KronSumConstruct(Block& L, Block& R, const std::vector<Term>& Terms, CSR* MatOutExplicit, KronSumShell* shell,
+                          Int rstart = -1, Int rend = -1) const;
     void KronSumSetUpShellTerms(KronSumShell& sh) const;
     void BuildTerms(const Block& L, const Block& R, const std::vector<Term>& TermsLR, std::vector<KronSumTerm>& out,
                     std::vector<CSR>& owned) const;
@@ -686,7 +687,7 @@ inline void KronBlocks_t::KronSumConstructExplicit(const Block& L, const Block& 
 
 /* src/DMRGKron.cpp:759-841.  Exactly one of MatOutExplicit / shell is non-null (do_shell switch). */
 inline void KronBlocks_t::KronSumConstruct(Block& L, Block& R, const std::vector<Term>& Terms, CSR* MatOutExplicit,
-                                           KronSumShell* shell) const {
+                                           KronSumShell* shell, Int rstart, Int rend) const {
     const Int nsites_left = L.NumSites(), nsites_right = R.NumSites(), nsites_out = nsites_left + nsites_right;
     Int Max_Isite = 0;
     for (const Term& t : Terms) { Max_Isite = std::max(Max_Isite, t.Isite); Max_Isite = std::max(Max_Isite, t.Jsite); }
@@ -711,8 +712,11 @@ inline void KronBlocks_t::KronSumConstruct(Block& L, Block& R, const std::vector
     if (CreateSmL && !L.init_Sm) L.CreateSm();
     if (CreateSmR && !R.init_Sm) R.CreateSm();
     if (shell) {
-        /* src/DMRGKron.cpp:1871-1917, one rank */
-        shell->Nrows = num_states; shell->rstart = 0; shell->lrows = num_states; shell->rend = num_states;
+        /* src/DMRGKron.cpp:1871-1917; [rstart,rend) is this "rank"'s row range (default: one rank owns all rows) */
+        shell->Nrows = num_states;
+        shell->rstart = rstart < 0 ? 0 : rstart;
+        shell->rend = rend < 0 ? num_states : rend;
+        shell->lrows = shell->rend - shell->rstart;
         BuildTerms(L, R, TermsLR, shell->Terms, shell->owned);
         KronSumSetUpShellTerms(*shell);
         /* the shell aliases operator rows, so Sm must outlive it: the caller destroys Sm after use */

@@ -34,11 +34,11 @@ def lib():
             build()
         L = C.CDLL(path)
         L.orc_last_error.restype = C.c_char_p
-        for name in ("orc_block_single_site", "orc_block_create", "orc_kron_eye", "orc_kron_create", "orc_shell_create",
+        for name in ("orc_block_single_site", "orc_block_create", "orc_kron_eye", "orc_kron_create", "orc_shell_create", "orc_shell_create_rows",
                      "orc_shell_create_single", "orc_truncate", "orc_rotate", "orc_dmrg_create", "orc_dmrg_block"):
             getattr(L, name).restype = C.c_void_p
         for name in ("orc_block_op_nnz", "orc_ham_terms", "orc_kron_size", "orc_kron_num_states", "orc_kron_map",
-                     "orc_kron_offsets_lr", "orc_shell_nterms", "orc_dmrg_nsteps", "orc_dmrg_step_nsectors"):
+                     "orc_kron_offsets_lr", "orc_shell_nterms", "orc_shell_lrows", "orc_dmrg_nsteps", "orc_dmrg_step_nsectors"):
             getattr(L, name).restype = LL
         L.orc_shell_fmas.restype = C.c_double
         L.orc_eigs.restype = C.c_double
@@ -214,10 +214,16 @@ class KronBlocks:
 
 
 class Shell:
-    def __init__(self, kb, terms=None, single=None):
+    def __init__(self, kb, terms=None, single=None, rows=None):
+        """rows=(r0, r1): build only that row range (what one MPI rank of the reference owns); apply() then returns
+        the lrows values of those rows."""
         self.kb = kb
         err = C.c_int(0)
-        if single is not None:
+        if rows is not None:
+            a, iop, isite, jop, jsite = terms_arrays(terms)
+            self.h = C.c_void_p(lib().orc_shell_create_rows(kb.h, len(terms), _p(a), _p(iop), _p(isite), _p(jop), _p(jsite),
+                                                            LL(rows[0]), LL(rows[1]), C.byref(err)))
+        elif single is not None:
             opl, il, opr, ir = single
             self.h = C.c_void_p(lib().orc_shell_create_single(kb.h, opl, LL(il), opr, LL(ir), C.byref(err)))
         else:
@@ -226,6 +232,7 @@ class Shell:
         if err.value:
             raise OracleError(err.value)
         self.n = kb.num_states()
+        self.lrows = lib().orc_shell_lrows(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -238,9 +245,9 @@ class Shell:
     def fmas(self):
         return lib().orc_shell_fmas(self.h)
 
-    def apply(self, x):
-        x = _d(x); y = np.zeros(self.n)
-        lib().orc_shell_apply(self.h, _p(x), _p(y))
+    def apply(self, x, nthreads=1):
+        x = _d(x); y = np.zeros(self.lrows)
+        lib().orc_shell_apply_rows(self.h, _p(x), _p(y), LL(0), LL(self.lrows), int(nthreads))
         return y
 
     def apply_rows(self, x, r0, r1, nthreads=1, y=None):

@@ -125,6 +125,20 @@ ll orc_kron_map(void* kb, ll l, ll r) { return ((KronBlocks_t*)kb)->Map(l, r); }
 ll orc_kron_offsets_lr(void* kb, ll l, ll r) { return ((KronBlocks_t*)kb)->Offsets(l, r); }
 
 /* ---- KronSumShell: KronSumConstruct (shell branch) + MatMult_KronSumShell ---- */
+/* rows [r0,r1) only (r0 < 0: all rows) — the row range one MPI rank of the reference would own; y of
+   orc_shell_apply* is then indexed from 0 = row r0 */
+void* orc_shell_create_rows(void* kbp, int nterms, const double* a, const int* iop, const ll* isite, const int* jop, const ll* jsite,
+                            ll r0, ll r1, int* err) {
+    KronBlocks_t* kb = (KronBlocks_t*)kbp;
+    Shell* s = new Shell();
+    s->L = const_cast<Block*>(&kb->LeftBlock);
+    s->R = const_cast<Block*>(&kb->RightBlock);
+    int e = guard([&] { kb->KronSumConstruct(*s->L, *s->R, make_terms(nterms, a, iop, isite, jop, jsite), nullptr, &s->sh, r0, r1); });
+    if (err) *err = e;
+    if (e) { delete s; return nullptr; }
+    return s;
+}
+ll orc_shell_lrows(void* s) { return ((Shell*)s)->sh.lrows; }
 void* orc_shell_create(void* kbp, int nterms, const double* a, const int* iop, const ll* isite, const int* jop, const ll* jsite, int* err) {
     KronBlocks_t* kb = (KronBlocks_t*)kbp;
     Shell* s = new Shell();

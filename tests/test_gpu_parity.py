@@ -1,0 +1,154 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, plus size-independent properties at larger sizes.  Tolerances: H·psi 1e-13 relative (per term), energies and
+truncation errors 1e-10 relative (north_star), bookkeeping bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import dmrgx_loader
+    P = dmrgx_loader.load_package()
+    P.use_library(None)  # the real CUDA library, nothing else
+    return P
+
+
+@pytest.fixture(scope="module")
+def ctx(P):
+    c = P.Context(0)
+    yield c
+    c.close()
+
+
+HEIS_CHAIN = dict(Lx=16, Ly=1, J1=0.5, Jz1=1.0, J2=0.0, Jz2=0.0, bcx=0, bcy=0)
+J1J2_CYL = dict(Lx=4, Ly=4, J1=0.5, Jz1=1.0, J2=0.25, Jz2=0.5)
+HEIS_CYL = dict(Lx=6, Ly=2, J1=0.5, Jz1=1.0, J2=0.0, Jz2=0.0)
+XY_CYL = dict(Lx=4, Ly=4, J1=1.0, Jz1=0.0, J2=1.0, Jz2=0.0)
+
+
+def test_native_library_is_loaded(P, ctx):
+    assert os.path.realpath(P.lib()._name) == os.path.realpath(P.LIB_PATH)
+    n0 = P.launch_count()
+    v = ctx.vec(10, np.arange(10.0))
+    assert v.get().tolist() == list(range(10))
+    b = P.Block.SingleSite(ctx)
+    assert b.NumStates() == 2
+    assert P.launch_count() >= n0
+
+
+def test_single_site_blocks(P, ctx, orc):
+    for spin in (1, 2):
+        pc.assert_blocks_equal(P, orc, P.Block.SingleSite(ctx, spin), orc.Block.single_site(spin), tol=0.0)
+
+
+@pytest.mark.parametrize("ham,nsys,nenv,mprep,mkeep", [
+    (HEIS_CHAIN, 3, 3, 8, 6),
+    (HEIS_CHAIN, 5, 3, 16, 12),
+    (HEIS_CHAIN, 7, 7, 24, 20),
+    (HEIS_CYL, 4, 4, 12, 10),
+    (J1J2_CYL, 5, 5, 20, 16),
+    (J1J2_CYL, 7, 7, 40, 32),
+    (XY_CYL, 7, 7, 32, 24),
+], ids=["chain-3+3", "chain-5+3", "chain-7+7", "cyl6x2-4+4", "j1j2-5+5", "j1j2-7+7", "xy-7+7"])
+def test_single_dmrg_step_matches_oracle(P, ctx, orc, ham, nsys, nenv, mprep, mkeep):
+    rng = np.random.default_rng(7)
+    pc.run_step_parity(P, orc, ctx, ham, nsys, nenv, mprep, mkeep, rng)
+
+
+@pytest.mark.parametrize("config,m", [("j1j2_12x6", 64), ("j1j2_12x6", 160), ("heis_8x4", 96), ("heis_chain24", 64), ("xy_16x8", 80)])
+def test_synthetic_workload_matvec_matches_oracle(P, ctx, orc, config, m):
+    """BASELINE.json configs on synthetic truncated blocks (bench_workload.py) at sizes the oracle finishes in seconds."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, config, m=m)
+    enl_o, kb_o = W.oracle_side(orc, wl)
+    pc.assert_blocks_equal(P, orc, wl.enl, enl_o, what="enlarged synthetic block")
+    pc.check_kron_bookkeeping(P, orc, wl.kron, kb_o)
+    osh = orc.Shell(kb_o, wl.terms)
+    pc.check_matvec(P, orc, ctx, wl.shell, osh, np.random.default_rng(3), nvec=2)
+
+
+def test_sparse_and_dense_tile_paths_agree(P, ctx, orc):
+    rng = np.random.default_rng(11)
+    ham = J1J2_CYL
+    d = orc.DMRG(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"])
+    d.warmup(24)
+    oL = orc.kron_eye(d.block(6), orc.Block.single_site(), pc.lr_terms(orc, ham, 8))
+    okb = orc.KronBlocks(oL, oL, [0.0])
+    terms = pc.lr_terms(orc, ham, 16)
+    osh = orc.Shell(okb, terms)
+    x = rng.standard_normal(osh.n)
+    y_ref = osh.apply(x)
+    try:
+        for thr in (0.0, 2.0):
+            ctx.set_dense_threshold(thr)
+            pL = pc.upload_block(P, ctx, oL, orc)
+            psh = P.KronBlocks(pL, pL, [0.0]).KronSumConstruct(terms)
+            y = psh.MatMult_host(x)
+            assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    finally:
+        ctx.set_dense_threshold(0.125)
+
+
+def test_full_size_properties_m2048(P, ctx):
+    """BASELINE.json's full size (12x6, m=2048): no oracle can run here, so check size-independent properties of H·psi:
+    linearity, symmetry <x|Hy> = <Hx|y>, and the Rayleigh quotient bound of the Lanczos result."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, "j1j2_12x6", m=2048)
+    H = wl.shell
+    n = wl.n
+    assert n > 1_000_000
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n); y = rng.standard_normal(n)
+    Hx = H.MatMult_host(x); Hy = H.MatMult_host(y)
+    Hxy = H.MatMult_host(2.0 * x - 3.0 * y)
+    scale = max(np.abs(Hx).max(), np.abs(Hy).max())
+    assert np.abs(Hxy - (2.0 * Hx - 3.0 * Hy)).max() <= 1e-11 * scale
+    assert abs(y @ Hx - x @ Hy) <= 1e-10 * np.linalg.norm(Hx) * np.linalg.norm(y)
+    e, psi, st = H.EPSSolve(tol=1e-6, max_it=3)
+    p = psi.get()
+    assert abs(np.linalg.norm(p) - 1.0) < 1e-10
+    ray = p @ H.MatMult_host(p)
+    assert abs(ray - e) <= 1e-8 * max(1.0, abs(e))
+    assert e < (x @ Hx) / (x @ x)  # below a random vector's Rayleigh quotient
+
+
+def test_truncate_rotate_roundtrip_properties(P, ctx):
+    """Synthetic m=256 step: U rows orthonormal, kept weights + truncation error = 1, rotated H symmetric."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, "heis_8x4", m=256)
+    e, psi, st = wl.shell.EPSSolve(tol=1e-10)
+    assert st["converged"]
+    btL, btR = P.GetTruncation(wl.kron, psi, 200)
+    for bt in (btL, btR):
+        U = bt.RotMatT()
+        assert np.abs(U @ U.T - np.eye(bt.m)).max() < 1e-10
+        ev, _ = bt.spectrum()
+        assert abs(ev.sum() - 1.0) < 1e-10
+        kept = np.sort(ev)[::-1][:bt.m]
+        assert abs((1.0 - kept[kept > 0].sum()) - bt.TruncErr) < 1e-12
+    new = P.RotateOperators(wl.enl, btL)
+    assert new.NumStates() == btL.m and new.CheckOperatorBlocks() == 0
+    Hn = new.get_operator_dense(P.OpH)
+    assert np.abs(Hn - Hn.T).max() < 1e-11
+    # spin-flip symmetry of the synthetic block is absent, but left/right truncations of the mirrored superblock agree
+    assert abs(btL.TruncErr - btR.TruncErr) < 1e-9
+
+
+def test_error_codes(P, ctx):
+    b = P.Block.Initialize(ctx, 2, [1.5, 0.5, -0.5, -1.5], [2, 3, 2, 1])
+    with pytest.raises(P.DmrgxError) as e:
+        b.set_operator(P.OpSz, 0, [0, 1, 1, 1, 1, 1, 1, 1, 1], [5], [1.0])  # row 0 (sector 0) -> column in sector 2
+    assert e.value.code == 63
+    with pytest.raises(P.DmrgxError):
+        P.Block.Initialize(ctx, 2, [0.5, 0.5], [1, 1])
+    with pytest.raises(P.DmrgxError) as e:
+        b.set_operator(P.OpSz, 7, [0] * 9, [], [])
+    assert e.value.code == 63
