@@ -206,8 +206,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     P.use_library(None)
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = P.Context(local, stream)
+    # a dedicated torch stream: the library launches on it and torch.cuda.Event records on it (the legacy default
+    # stream has handle 0, which the C ABI reads as "create a private stream" — events would then miss the kernels)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    assert tstream.cuda_stream != 0
+    ctx = P.Context(local, tstream.cuda_stream)
     wl = W.Workload(P, ctx, args.config, m=args.m)
     H = wl.shell
     st = H.stats()
