@@ -119,7 +119,11 @@ struct Kron {
 struct Plan {
     std::vector<dev::WorkItem> items;
     std::vector<dev::Segment> segs;
-    BufRef d_items, d_segs;
+    std::vector<dev::ReduceItem> reduces;   /* split chains: partial tiles in the scratch, summed in a second launch */
+    long long scratch_elems = 0;
+    /* when > 0, emit_cells cuts chains whose cost (sum of K) times tile area exceeds this many multiply-adds */
+    double split_item_cost = 0;
+    BufRef d_items, d_segs, d_reduces, scratch;
     void upload(Ctx* ctx);
     void run(Ctx* ctx, const double* x = nullptr, double* y = nullptr) const;
     /* useful work of the plan: 2*M*N*K of GEMM segments actually inside tile extents */

@@ -52,7 +52,7 @@ struct WorkItem {
     int tm, tn;           /* extents, 1..TILE */
     int seg_begin, seg_end;
     int mode;             /* 0: store (C = acc), 1: atomic accumulate (C += acc) */
-    int c_in_y;           /* 1: C holds a BYTE OFFSET into the y vector of the launch */
+    int c_in_y;           /* 0: C is a pointer; 1: C holds a BYTE OFFSET into the y vector of the launch; 2: into the w scratch */
 };
 
 constexpr int TILE = 64;  /* maximum tile extent of a work item */
@@ -80,7 +80,21 @@ long long launch_count();
 /* chain contraction engine */
 /* x / y: base pointers that offset-typed operands (SEGF_*_X, c_in_y) are relative to, so one plan serves any
    pair of device vectors (the Lanczos basis vectors change every step; the plan does not). */
-void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y);
+void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y, double* w = nullptr);
+
+/* Long accumulation chains are cut into parts that write partial tiles to the w scratch (so that a launch has enough
+   equal work items to fill 148 SMs several times over); the parts are then summed in a FIXED order — deterministic,
+   no atomics.  dst: byte offset into y (dst_in_y) or pointer; part p of the tile is the row-major tm×tn panel at
+   w + src_off/8 + p*tm*tn. */
+struct ReduceItem {
+    double* dst;
+    long long ldc;
+    long long src_off;   /* bytes into w */
+    int tm, tn;
+    int nparts;
+    int dst_in_y;
+};
+void run_reduce(Stream*, const ReduceItem* d_items, int nitems, double* y, const double* w);
 
 /* vector kernels of the thick-restart Lanczos (all results stay on the device) */
 void fill_random(Stream*, double* x, long long n, unsigned long long seed);

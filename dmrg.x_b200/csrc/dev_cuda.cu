@@ -138,64 +138,137 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-/* stage one K-chunk of both operands into shared memory */
-__device__ __forceinline__ void load_chunk(double* As, double* Bs, const double* __restrict__ Ab, const double* __restrict__ Bb,
-                                           long long lda_m, long long lda_k, long long ldb_n, long long ldb_k, int tm, int tn, int k0,
-                                           int K, bool a_mk, bool b_nk, int tid) {
-    if (a_mk) { /* contiguous along k: As[m][k] */
+/* ---- operand staging ------------------------------------------------------------------------
+ *  Each thread owns 8 elements of the A chunk and 8 of the B chunk.  Rows beyond the tile extent are
+ *  CLAMPED to the last valid row (their products land in accumulator rows that are never stored), so
+ *  the only predicate is the K tail, and the global pointers are bumped by a constant per chunk.
+ *  Layout template parameters make every shared-memory offset an immediate.                       */
+template <bool MK> /* MK: operand contiguous along k -> smem [row][k]; else contiguous along row -> smem [k][row] */
+struct Stager {
+    const double* base;  /* bumped by kstep per chunk */
+    int off[8];          /* element offsets of this thread's 8 elements (rows clamped to the tile extent) */
+    long long kstep;     /* pointer advance per chunk, in elements */
+    int soff;            /* smem offset of element 0; element i is at soff + i*SI */
+    int k0;              /* k index of element 0 inside a chunk (element i: k0 for MK, k0 + 2i otherwise) */
+    static constexpr int SI = MK ? 8 * S_MK : 2 * S_KM;
+    __device__ __forceinline__ void init(const double* b, long long ld_row, long long ld_k, int ext, int tid) {
+        base = b;
+        if (MK) {
+            const int k = tid & 15, r0 = tid >> 4;
 #pragma unroll
-        for (int i = 0; i < (BM * BK) / NTHREADS; ++i) {
-            int idx = tid + i * NTHREADS;
-            int m = idx / BK, k = idx % BK;
-            bool v = (m < tm) && (k0 + k < K);
-            const double* src = v ? (Ab + (long long)m * lda_m + (long long)(k0 + k) * lda_k) : Ab;
-            cp_async8(As + m * S_MK + k, src, v);
-        }
-    } else { /* contiguous along m: As[k][m] */
+            for (int i = 0; i < 8; ++i) {
+                int r = r0 + 8 * i; r = r < ext ? r : ext - 1;
+                off[i] = (int)(r * ld_row + k * ld_k);
+            }
+            soff = r0 * S_MK + k;
+            k0 = k;
+        } else {
+            const int r = tid & 63, kk = tid >> 6;
+            const int rc = r < ext ? r : ext - 1;
 #pragma unroll
-        for (int i = 0; i < (BM * BK) / NTHREADS; ++i) {
-            int idx = tid + i * NTHREADS;
-            int k = idx / BM, m = idx % BM;
-            bool v = (m < tm) && (k0 + k < K);
-            const double* src = v ? (Ab + (long long)m * lda_m + (long long)(k0 + k) * lda_k) : Ab;
-            cp_async8(As + k * S_KM + m, src, v);
+            for (int i = 0; i < 8; ++i) off[i] = (int)(rc * ld_row + (kk + 2 * i) * ld_k);
+            soff = kk * S_KM + r;
+            k0 = kk;
         }
+        kstep = (long long)BK * ld_k;
     }
-    if (b_nk) { /* contiguous along k: Bs[n][k] */
+    /* krem = K - k0 of this chunk (>= 1) */
+    __device__ __forceinline__ void issue(double* sm, int krem) {
+        if (krem >= BK) {
 #pragma unroll
-        for (int i = 0; i < (BN * BK) / NTHREADS; ++i) {
-            int idx = tid + i * NTHREADS;
-            int n = idx / BK, k = idx % BK;
-            bool v = (n < tn) && (k0 + k < K);
-            const double* src = v ? (Bb + (long long)n * ldb_n + (long long)(k0 + k) * ldb_k) : Bb;
-            cp_async8(Bs + n * S_MK + k, src, v);
-        }
-    } else { /* contiguous along n: Bs[k][n] */
+            for (int i = 0; i < 8; ++i) cp_async8(sm + soff + i * SI, base + off[i], true);
+        } else {
 #pragma unroll
-        for (int i = 0; i < (BN * BK) / NTHREADS; ++i) {
-            int idx = tid + i * NTHREADS;
-            int k = idx / BN, n = idx % BN;
-            bool v = (n < tn) && (k0 + k < K);
-            const double* src = v ? (Bb + (long long)n * ldb_n + (long long)(k0 + k) * ldb_k) : Bb;
-            cp_async8(Bs + k * S_KM + n, src, v);
+            for (int i = 0; i < 8; ++i) {
+                const bool v = (MK ? k0 : k0 + 2 * i) < krem;
+                cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
+            }
         }
+        base += kstep;
+    }
+};
+
+template <bool A_MK, bool B_NK, int NMI>
+__device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
+                                             int tid, int rbase, int cbase, int g, int t, int nni) {
+    Stager<A_MK> sa;
+    Stager<B_NK> sb;
+    sa.init(sg.A + (long long)it.m0 * sg.lda_m, sg.lda_m, sg.lda_k, it.tm, tid);
+    sb.init(sg.B + (long long)it.n0 * sg.ldb_n, sg.ldb_n, sg.ldb_k, it.tn, tid);
+    const int K = sg.K;
+    const int nchunks = (K + BK - 1) / BK;
+    const double coef = sg.coef;
+    constexpr int a_sm = A_MK ? S_MK : 1, a_sk = A_MK ? 1 : S_KM;
+    constexpr int b_sn = B_NK ? S_MK : 1, b_sk = B_NK ? 1 : S_KM;
+    const int a_base = (rbase + g) * a_sm + t * a_sk;
+    const int b_base = (cbase + g) * b_sn + t * b_sk;
+    __syncthreads(); /* the previous segment's readers are done with both stages */
+    sa.issue(As, K);
+    sb.issue(Bs, K);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        const int cur = c & 1;
+        if (c + 1 < nchunks) {
+            const int krem = K - (c + 1) * BK;
+            sa.issue(As + (cur ^ 1) * SMEM_TILE, krem);
+            sb.issue(Bs + (cur ^ 1) * SMEM_TILE, krem);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* as = As + cur * SMEM_TILE + a_base;
+        const double* bs = Bs + cur * SMEM_TILE + b_base;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[NMI];
+#pragma unroll
+            for (int mi = 0; mi < NMI; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                if (ni < nni) { /* warp-uniform branch; the coefficient rides on the B fragment (1 DMUL per 4 DMMA) */
+                    const double b = bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
+#pragma unroll
+                    for (int mi = 0; mi < NMI; ++mi) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool A_MK, bool B_NK>
+__device__ __forceinline__ void gemm_dispatch(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
+                                              int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
+    /* nmi is warp-uniform but differs between the two warp rows of an edge tile: every warp must still take part in
+       the staging and the barriers, so a warp without rows runs the 1-fragment variant on clamped (duplicate) rows */
+    switch (nmi) {
+        case 4: gemm_segment<A_MK, B_NK, 4>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
+        case 3: gemm_segment<A_MK, B_NK, 3>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
+        case 2: gemm_segment<A_MK, B_NK, 2>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
+        default: gemm_segment<A_MK, B_NK, 1>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi > 0 ? nni : 0); break;
     }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __restrict__ items, const Segment* __restrict__ segs,
-                                                         const double* __restrict__ xbase, double* __restrict__ ybase) {
-    __shared__ double As[2][SMEM_TILE];
-    __shared__ double Bs[2][SMEM_TILE];
+                                                            const double* __restrict__ xbase, double* __restrict__ ybase,
+                                                            double* __restrict__ wbase) {
+    __shared__ double As[2 * SMEM_TILE];
+    __shared__ double Bs[2 * SMEM_TILE];
     WorkItem it = items[blockIdx.x];
-    if (it.c_in_y) it.C = (double*)((char*)ybase + (size_t)it.C);
+    if (it.c_in_y) it.C = (double*)((char*)(it.c_in_y == 1 ? ybase : wbase) + (size_t)it.C);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
     const int g = lane >> 2, t = lane & 3;
     const int tm = it.tm, tn = it.tn;
-    /* number of valid 8-row / 8-col fragments of this warp (warp-uniform) */
-    int nmi = (tm - wm * 32 + 7) / 8; nmi = nmi < 0 ? 0 : (nmi > 4 ? 4 : nmi);
-    int nni = (tn - wn * 32 + 7) / 8; nni = nni < 0 ? 0 : (nni > 4 ? 4 : nni);
+    /* the tile is split evenly between the two warp rows / columns (plan.cpp makes extents multiples of 16 except at
+       the ragged edge): rows [rbase, rbase + 8*nmi) and columns [cbase, cbase + 8*nni) belong to this warp */
+    const int hm = ((tm + 15) >> 4) << 3, hn = ((tn + 15) >> 4) << 3;
+    const int rbase = wm * hm, cbase = wn * hn;
+    int nmi = (tm - rbase + 7) / 8; nmi = nmi < 0 ? 0 : (nmi > (hm >> 3) ? (hm >> 3) : nmi);
+    int nni = (tn - cbase + 7) / 8; nni = nni < 0 ? 0 : (nni > (hn >> 3) ? (hn >> 3) : nni);
 
     double acc[4][4][2];
 #pragma unroll
@@ -208,58 +281,27 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
         if (sg.flags & SEGF_A_X) sg.A = (const double*)((const char*)xbase + (size_t)sg.A);
         if (sg.flags & SEGF_B_X) sg.B = (const double*)((const char*)xbase + (size_t)sg.B);
         if (sg.type == SEG_GEMM) {
-            const double* Ab = sg.A + (long long)it.m0 * sg.lda_m;
-            const double* Bb = sg.B + (long long)it.n0 * sg.ldb_n;
             const bool a_mk = (sg.lda_k == 1) || (sg.lda_m != 1);
             const bool b_nk = (sg.ldb_k == 1) || (sg.ldb_n != 1);
-            const int K = sg.K;
-            const int nchunks = (K + BK - 1) / BK;
-            const double coef = sg.coef;
-            const int a_sm = a_mk ? S_MK : 1, a_sk = a_mk ? 1 : S_KM;
-            const int b_sn = b_nk ? S_MK : 1, b_sk = b_nk ? 1 : S_KM;
-            __syncthreads(); /* previous segment's readers are done with both stages */
-            load_chunk(As[0], Bs[0], Ab, Bb, sg.lda_m, sg.lda_k, sg.ldb_n, sg.ldb_k, tm, tn, 0, K, a_mk, b_nk, tid);
-            cp_async_commit();
-            for (int c = 0; c < nchunks; ++c) {
-                const int cur = c & 1;
-                if (c + 1 < nchunks) {
-                    load_chunk(As[cur ^ 1], Bs[cur ^ 1], Ab, Bb, sg.lda_m, sg.lda_k, sg.ldb_n, sg.ldb_k, tm, tn, (c + 1) * BK, K, a_mk,
-                               b_nk, tid);
-                    cp_async_commit();
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                const double* as = As[cur] + (wm * 32 + g) * a_sm + t * a_sk;
-                const double* bs = Bs[cur] + (wn * 32 + g) * b_sn + t * b_sk;
-#pragma unroll
-                for (int kk = 0; kk < BK / 4; ++kk) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = (mi < nmi) ? as[mi * 8 * a_sm + kk * 4 * a_sk] * coef : 0.0;
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) b[ni] = (ni < nni) ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : 0.0;
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni)
-                            if (mi < nmi && ni < nni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                }
-                __syncthreads();
+            if (a_mk) {
+                if (b_nk) gemm_dispatch<true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                else gemm_dispatch<true, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+            } else {
+                if (b_nk) gemm_dispatch<false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                else gemm_dispatch<false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
             }
         } else {
             /* slow-path segments: each thread updates the accumulator elements it owns */
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
-                const int row = wm * 32 + mi * 8 + g;
-                if (row >= tm) continue;
+                const int row = rbase + mi * 8 + g;
+                if (mi >= nmi || row >= tm) continue;
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int col = wn * 32 + ni * 8 + 2 * t + h;
-                        if (col >= tn) continue;
+                        const int col = cbase + ni * 8 + 2 * t + h;
+                        if (ni >= nni || col >= tn) continue;
                         const long long gm = it.m0 + row, gn = it.n0 + col;
                         double v = 0.0;
                         if (sg.type == SEG_AXPY) {
@@ -288,14 +330,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
     /* epilogue: each element written exactly once */
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-        const int row = wm * 32 + mi * 8 + g;
-        if (row >= tm) continue;
+        const int row = rbase + mi * 8 + g;
+        if (mi >= nmi || row >= tm) continue;
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = wn * 32 + ni * 8 + 2 * t + h;
-                if (col >= tn) continue;
+                const int col = cbase + ni * 8 + 2 * t + h;
+                if (ni >= nni || col >= tn) continue;
                 double* p = it.C + (long long)row * it.ldc + col;
                 if (it.mode == 0) *p = acc[mi][ni][h];
                 else atomicAdd(p, acc[mi][ni][h]);
@@ -304,9 +346,26 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
     }
 }
 
-void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y) {
+void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y, double* w) {
     if (nitems <= 0) return;
-    chain_kernel<<<nitems, NTHREADS, 0, st->s>>>(d_items, d_segs, x, y);
+    chain_kernel<<<nitems, NTHREADS, 0, st->s>>>(d_items, d_segs, x, y, w);
+    LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceItem* __restrict__ items, double* __restrict__ ybase, const double* __restrict__ wbase) {
+    const ReduceItem it = items[blockIdx.x];
+    double* dst = it.dst_in_y ? (double*)((char*)ybase + (size_t)it.dst) : it.dst;
+    const double* src = (const double*)((const char*)wbase + it.src_off);
+    const int cnt = it.tm * it.tn;
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+        double v = src[e];
+        for (int p = 1; p < it.nparts; ++p) v += src[(long long)p * cnt + e]; /* fixed order: deterministic */
+        dst[(long long)(e / it.tn) * it.ldc + (e % it.tn)] = v;
+    }
+}
+void run_reduce(Stream* st, const ReduceItem* d_items, int nitems, double* y, const double* w) {
+    if (nitems <= 0) return;
+    reduce_kernel<<<nitems, 256, 0, st->s>>>(d_items, y, w);
     LAUNCH_CHECK();
 }
 

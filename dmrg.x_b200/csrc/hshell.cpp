@@ -206,6 +206,15 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
             if (!vcontrib.empty()) emit_cells(H->stage1, W + gp[g][p].voff, false, nRq, nLp, nRq, vcontrib, false);
         }
     }
+    {   /* dry run to learn the total stage-2 work, then cut long chains so that the launch has ~5 waves of
+           equal items on 148 SMs x 3 resident CTAs (v0 lost a third of the machine to a 1.4-wave tail) */
+        Plan dry;
+        for (int p = 0; p < np; ++p)
+            emit_cells(dry, yoff(kron->off[p]), true, SR.size[kron->pairs[p].ir], SL.size[kron->pairs[p].il], SR.size[kron->pairs[p].ir],
+                       ycontrib[p], true);
+        const double target_items = 148.0 * 3.0 * 5.0;
+        if (dry.flops > 0 && (double)dry.items.size() < target_items) H->stage2.split_item_cost = 0.5 * dry.flops / target_items;
+    }
     for (int p = 0; p < np; ++p) {
         const int nLp = SL.size[kron->pairs[p].il], nRp = SR.size[kron->pairs[p].ir];
         emit_cells(H->stage2, yoff(kron->off[p]), true, nRp, nLp, nRp, ycontrib[p], true);

@@ -5,6 +5,7 @@
  *  cell is tiled with (almost) equal tiles of at most dev::TILE × dev::TILE.
  */
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "common.h"
@@ -31,12 +32,19 @@ void Plan::upload(Ctx* ctx) {
     d_segs = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, segs.size()) * sizeof(dev::Segment));
     dev::h2d(ctx->st, d_items->p, items.data(), items.size() * sizeof(dev::WorkItem));
     dev::h2d(ctx->st, d_segs->p, segs.data(), segs.size() * sizeof(dev::Segment));
+    if (!reduces.empty()) {
+        d_reduces = std::make_shared<DevBuf>(ctx, reduces.size() * sizeof(dev::ReduceItem));
+        dev::h2d(ctx->st, d_reduces->p, reduces.data(), reduces.size() * sizeof(dev::ReduceItem));
+        scratch = std::make_shared<DevBuf>(ctx, (size_t)scratch_elems * 8);
+    }
     dev::sync(ctx->st); /* the host vectors may be reallocated by the caller afterwards */
 }
 
 void Plan::run(Ctx* ctx, const double* x, double* y) const {
     if (items.empty()) return;
-    dev::run_chain(ctx->st, d_items->as<dev::WorkItem>(), (int)items.size(), d_segs->as<dev::Segment>(), x, y);
+    double* w = scratch ? scratch->as<double>() : nullptr;
+    dev::run_chain(ctx->st, d_items->as<dev::WorkItem>(), (int)items.size(), d_segs->as<dev::Segment>(), x, y, w);
+    if (!reduces.empty()) dev::run_reduce(ctx->st, d_reduces->as<dev::ReduceItem>(), (int)reduces.size(), y, w);
 }
 
 static inline const double* padd(const double* p, long long elems) { return p + elems; }
@@ -78,24 +86,74 @@ void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Nc
             const int seg_end = (int)plan.segs.size();
             if (seg_end == seg_begin && !cover_all) continue;
             const int M = r1 - r0, N = c1 - c0;
-            const int nmt = (M + dev::TILE - 1) / dev::TILE, nnt = (N + dev::TILE - 1) / dev::TILE;
-            /* balanced extents, multiples of 8 (the DMMA fragment edge) */
-            const int tm = std::min(dev::TILE, ((M + nmt - 1) / nmt + 7) / 8 * 8);
-            const int tn = std::min(dev::TILE, ((N + nnt - 1) / nnt + 7) / 8 * 8);
-            for (int m0 = 0; m0 < M; m0 += tm)
-                for (int n0 = 0; n0 < N; n0 += tn) {
+            /* tile extents in units of 16 rows/cols (two 8-row DMMA fragments, one per warp row), spread as evenly as
+               possible over ceil(units/4) tiles: every tile is 64 or 48 (or less, for small cells) wide, and the two
+               warp rows / columns of a CTA carry the same number of fragments */
+            auto split = [](int len) {
+                std::vector<int> ext;
+                const int units = (len + 15) / 16;
+                const int ntile = (units + 3) / 4;
+                int left = len;
+                for (int i = 0; i < ntile; ++i) {
+                    const int u = units / ntile + (i < units % ntile ? 1 : 0);
+                    const int e = std::min(left, u * 16);
+                    ext.push_back(e);
+                    left -= e;
+                }
+                return ext;
+            };
+            const std::vector<int> em = split(M), en = split(N);
+            /* cut a long chain into parts of roughly equal K (whole segments only) */
+            std::vector<int> part_begin = {seg_begin};
+            if (plan.split_item_cost > 0 && seg_end - seg_begin > 1) {
+                double ktot = 0;
+                for (int sgi = seg_begin; sgi < seg_end; ++sgi) ktot += plan.segs[sgi].type == dev::SEG_GEMM ? plan.segs[sgi].K : 0;
+                const double area = (double)em[0] * (double)en[0];
+                int nparts = (int)std::ceil(ktot * area / plan.split_item_cost);
+                nparts = std::max(1, std::min(nparts, seg_end - seg_begin));
+                if (nparts > 1) {
+                    double acc = 0;
+                    int next = 1;
+                    for (int sgi = seg_begin; sgi < seg_end && next < nparts; ++sgi) {
+                        acc += plan.segs[sgi].type == dev::SEG_GEMM ? plan.segs[sgi].K : 0;
+                        if (acc >= ktot * next / nparts && sgi + 1 < seg_end) { part_begin.push_back(sgi + 1); ++next; }
+                    }
+                }
+            }
+            part_begin.push_back(seg_end);
+            const int nparts = (int)part_begin.size() - 1;
+            int m0 = 0;
+            for (int tm : em) {
+                int n0 = 0;
+                for (int tn : en) {
                     dev::WorkItem it;
                     std::memset(&it, 0, sizeof it);
-                    it.C = C + (long long)(r0 + m0) * ldc + (c0 + n0);
-                    it.ldc = ldc;
                     it.m0 = m0; it.n0 = n0;
-                    it.tm = std::min(tm, M - m0);
-                    it.tn = std::min(tn, N - n0);
-                    it.seg_begin = seg_begin; it.seg_end = seg_end;
+                    it.tm = tm; it.tn = tn;
                     it.mode = 0;
-                    it.c_in_y = c_in_y ? 1 : 0;
-                    plan.items.push_back(it);
+                    double* dst = C + (long long)(r0 + m0) * ldc + (c0 + n0);
+                    if (nparts == 1) {
+                        it.C = dst; it.ldc = ldc; it.c_in_y = c_in_y ? 1 : 0;
+                        it.seg_begin = seg_begin; it.seg_end = seg_end;
+                        plan.items.push_back(it);
+                    } else {
+                        dev::ReduceItem ri;
+                        std::memset(&ri, 0, sizeof ri);
+                        ri.dst = dst; ri.ldc = ldc; ri.dst_in_y = c_in_y ? 1 : 0;
+                        ri.src_off = plan.scratch_elems * 8; ri.tm = tm; ri.tn = tn; ri.nparts = nparts;
+                        plan.reduces.push_back(ri);
+                        for (int pp = 0; pp < nparts; ++pp) {
+                            it.C = (double*)(uintptr_t)((plan.scratch_elems + (long long)pp * tm * tn) * 8);
+                            it.ldc = tn; it.c_in_y = 2;
+                            it.seg_begin = part_begin[pp]; it.seg_end = part_begin[pp + 1];
+                            plan.items.push_back(it);
+                        }
+                        plan.scratch_elems += (long long)nparts * tm * tn;
+                    }
+                    n0 += tn;
                 }
+                m0 += tm;
+            }
             plan.flops += kflops * (double)M * (double)N;
         }
     }

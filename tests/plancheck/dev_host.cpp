@@ -38,12 +38,12 @@ void d2d(Stream*, void* d, const void* s, size_t b) { if (b) std::memmove(d, s, 
 void memset0(Stream*, void* d, size_t b) { if (b) std::memset(d, 0, b); }
 void sync(Stream*) {}
 
-void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, const double* xbase, double* ybase) {
+void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, const double* xbase, double* ybase, double* wbase) {
     ++g_launches;
     std::vector<double> acc;
     for (int w = 0; w < nitems; ++w) {
         WorkItem it = items[w];
-        if (it.c_in_y) it.C = (double*)((char*)ybase + (size_t)it.C);
+        if (it.c_in_y) it.C = (double*)((char*)(it.c_in_y == 1 ? ybase : wbase) + (size_t)it.C);
         if (it.tm < 1 || it.tn < 1 || it.tm > TILE || it.tn > TILE) throw std::runtime_error("bad tile extents");
         acc.assign((size_t)it.tm * it.tn, 0.0);
         for (int s = it.seg_begin; s < it.seg_end; ++s) {
@@ -82,6 +82,21 @@ void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, 
                 double* p = it.C + (long long)m * it.ldc + n;
                 if (it.mode == 0) *p = acc[(size_t)m * it.tn + n]; else *p += acc[(size_t)m * it.tn + n];
             }
+    }
+}
+
+void run_reduce(Stream*, const ReduceItem* items, int nitems, double* ybase, const double* wbase) {
+    ++g_launches;
+    for (int i = 0; i < nitems; ++i) {
+        const ReduceItem& it = items[i];
+        double* dst = it.dst_in_y ? (double*)((char*)ybase + (size_t)it.dst) : it.dst;
+        const double* src = (const double*)((const char*)wbase + it.src_off);
+        const int cnt = it.tm * it.tn;
+        for (int e = 0; e < cnt; ++e) {
+            double v = src[e];
+            for (int p = 1; p < it.nparts; ++p) v += src[(long long)p * cnt + e];
+            dst[(long long)(e / it.tn) * it.ldc + (e % it.tn)] = v;
+        }
     }
 }
 
