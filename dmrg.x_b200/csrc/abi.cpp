@@ -116,6 +116,16 @@ int dmrgx_hshell_create_single(dmrgx_kron k, int opl, dmrgx_int il, int opr, dmr
     *out = nullptr;
     return guard([&] { *out = (dmrgx_hshell)hshell_create_single(K(k), opl, (int)il, opr, (int)ir); });
 }
+int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, const dmrgx_int* lsite, dmrgx_int nr, const int* rop,
+                                const dmrgx_int* rsite, dmrgx_hshell* out) {
+    *out = nullptr;
+    return guard([&] {
+        std::vector<std::pair<int, int>> l, r;
+        for (dmrgx_int i = 0; i < nl; ++i) l.push_back({lop[i], (int)lsite[i]});
+        for (dmrgx_int i = 0; i < nr; ++i) r.push_back({rop[i], (int)rsite[i]});
+        *out = (dmrgx_hshell)hshell_create_product(K(k), l, r);
+    });
+}
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y) { return guard([&] { hshell_apply(H(h), d_x, d_y); }); }
 int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y) {
     return guard([&] {

@@ -139,6 +139,7 @@ struct HShell {
     BufRef xbuf, ybuf;           /* device staging of the host-buffer entry point */
     void* h_pinned = nullptr;
     std::vector<BufRef> keep;    /* pre-summed right factors etc. */
+    std::vector<std::shared_ptr<Operator>> keep_ops; /* operator products of correlators */
     long long alg_bytes = 0;     /* 16*D + distinct operator tile bytes */
     double alg_flops = 0;
     int nterms = 0;
@@ -172,6 +173,7 @@ Kron* kron_create(const Block* L, const Block* R, const std::vector<double>& qn_
 
 HShell* hshell_create(const Kron*, const std::vector<Term>& terms);
 HShell* hshell_create_single(const Kron*, int opl, int il, int opr, int ir);
+HShell* hshell_create_product(const Kron*, const std::vector<std::pair<int, int>>& lops, const std::vector<std::pair<int, int>>& rops);
 void hshell_apply(HShell*, const double* d_x, double* d_y);
 
 struct EigsOpts { double tol = 1e-8; int ncv = 16; int max_it = 0; unsigned long long seed = 20261018ULL; };

@@ -271,6 +271,98 @@ HShell* hshell_create_single(const Kron* kron, int opl, int il, int opr, int ir)
     return build_shell(kron, groups, 1);
 }
 
+/* Product O_1·O_2·…·O_k of operators of ONE block (CalculateOperatorProducts, include/DMRGBlockContainer.hpp:2340-2425:
+   MatMatMult chain in list order), built right to left on the device as dense sector panels: any tile format may
+   stand on the left (dense -> DMMA GEMM, CSR -> CSRA, scaled identity -> AXPY) of the dense running product. */
+static std::shared_ptr<Operator> operator_product(const Block* blk, const std::vector<std::pair<int, int>>& ops, std::vector<BufRef>& keep) {
+    Ctx* ctx = blk->ctx;
+    const Sectors& S = blk->sec;
+    const int ns = S.nsec();
+    std::shared_ptr<Operator> P;
+    for (int k = (int)ops.size() - 1; k >= 0; --k) {
+        const Operator* O = blk->op(ops[k].first, ops[k].second);
+        std::shared_ptr<Operator> N = std::make_shared<Operator>();
+        N->shift = O->shift + (P ? P->shift : 0);
+        N->present = true;
+        N->tiles.assign(ns, {});
+        std::vector<long long> off(ns + 1, 0);
+        for (int I = 0; I < ns; ++I) {
+            const int J = I + N->shift;
+            off[I + 1] = off[I] + ((J >= 0 && J < ns) ? (long long)S.size[I] * S.size[J] : 0);
+        }
+        BufRef buf = std::make_shared<DevBuf>(ctx, std::max<long long>(1, off[ns]) * 8);
+        keep.push_back(buf);
+        Plan plan;
+        for (int I = 0; I < ns; ++I) {
+            const int J = I + N->shift, M = I + O->shift; /* O: I -> M, P: M -> J */
+            if (J < 0 || J >= ns || S.size[I] == 0 || S.size[J] == 0) continue;
+            double* out = buf->as<double>() + off[I];
+            const int nI = S.size[I], nJ = S.size[J];
+            std::vector<Contribution> cs;
+            if (M >= 0 && M < ns) {
+                for (const Tile& a : O->tiles[I]) {
+                    const int ra0 = a.r0 - S.off[I], ca0 = a.c0 - S.off[M];
+                    if (!P) { cs.push_back(add_tile_contribution(a, ra0, ca0, 1.0)); continue; }
+                    for (const Tile& b : P->tiles[M]) { /* one dense panel covering the whole (M,J) block */
+                        Contribution c;
+                        c.r0 = ra0; c.c0 = 0; c.nr = a.nr; c.nc = nJ;
+                        const double* bsrc = b.d + (long long)ca0 * nJ;
+                        if (a.fmt == T_DENSE) {
+                            c.seg = make_seg(dev::SEG_GEMM);
+                            c.seg.A = a.d; c.seg.lda_m = a.sr; c.seg.lda_k = a.sc; c.seg.K = a.nc;
+                            c.seg.B = bsrc; c.seg.ldb_k = nJ; c.seg.ldb_n = 1;
+                        } else if (a.fmt == T_EYE) {
+                            c.seg = make_seg(dev::SEG_AXPY);
+                            c.seg.A = bsrc; c.seg.lda_m = nJ; c.seg.lda_k = 1; c.seg.coef = a.scale;
+                        } else {
+                            c.seg = make_seg(dev::SEG_CSRA);
+                            c.seg.rowptr = a.rowptr; c.seg.colidx = a.col; c.seg.B = a.val;
+                            c.seg.A = bsrc; c.seg.ldb_k = nJ; c.seg.ldb_n = 1;
+                        }
+                        cs.push_back(c);
+                    }
+                }
+            }
+            emit_cells(plan, out, false, nJ, nI, nJ, cs, true);
+            Tile t;
+            t.fmt = T_DENSE; t.r0 = S.off[I]; t.c0 = S.off[J]; t.nr = nI; t.nc = nJ; t.d = out; t.sr = nJ; t.sc = 1; t.owner = buf;
+            N->tiles[I].push_back(t);
+        }
+        plan.upload(ctx);
+        plan.run(ctx);
+        dev::sync(ctx->st); /* the plan's device lists die with this scope */
+        P = N;
+    }
+    return P;
+}
+
+/* correlator shell: 1.0 · (Π SysOps) ⊗ (Π EnvOps), include/DMRGBlockContainer.hpp:2262-2296.  An empty list is the
+   identity; a single operator is used in place; longer lists are multiplied out on the device first. */
+HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int, int>>& lops, const std::vector<std::pair<int, int>>& rops) {
+    std::vector<BufRef> keep;
+    std::vector<std::shared_ptr<Operator>> keep_ops;
+    auto factor = [&](const Block* blk, const std::vector<std::pair<int, int>>& ops, int& shift) -> const Operator* {
+        shift = 0;
+        for (auto& o : ops) {
+            if (o.first < OP_SM || o.first > OP_SP) throw Err(ERR_ARG_WRONG, "Incorrect operator type.");
+            shift += o.first;
+        }
+        if (ops.empty()) return nullptr;
+        if (ops.size() == 1) return blk->op(ops[0].first, ops[0].second);
+        keep_ops.push_back(operator_product(blk, ops, keep));
+        return keep_ops.back().get();
+    };
+    int sA = 0, sB = 0;
+    const Operator* A = factor(kron->L, lops, sA);
+    const Operator* B = factor(kron->R, rops, sB);
+    std::vector<Group> groups;
+    groups.push_back({A, sA, sB, {{1.0, B}}});
+    HShell* H = build_shell(kron, groups, 1);
+    H->keep.insert(H->keep.end(), keep.begin(), keep.end());
+    H->keep_ops = keep_ops;
+    return H;
+}
+
 /* MatMult_KronSumShell, src/DMRGKron.cpp:1827-1869 */
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
     H->stage1.run(H->ctx, d_x, nullptr);

@@ -90,6 +90,11 @@ int dmrgx_hshell_create(dmrgx_kron k, dmrgx_int nterms, const double* a, const i
 /* KronConstruct(Mat_L, OpType_L, Mat_R, OpType_R, MatOut): include/DMRGKron.hpp:309 — one term 1.0·A⊗B; an op of
    DMRGX_OP_EYE means identity on that side */
 int dmrgx_hshell_create_single(dmrgx_kron k, int op_left, dmrgx_int isite_left, int op_right, dmrgx_int isite_right, dmrgx_hshell* out);
+/* correlator operator 1.0 · (O_1·…·O_nl on the left block) ⊗ (O'_1·…·O'_nr on the right block): CalculateOperatorProducts
+   (MatMatMult chain in list order) + KronConstruct, include/DMRGBlockContainer.hpp:2262-2296, 2340-2425.  An empty
+   list is the identity; ops are DMRGX_OP_SM / SZ / SP, sites are block-local. */
+int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, const dmrgx_int* lsite, dmrgx_int nr, const int* rop,
+                                const dmrgx_int* rsite, dmrgx_hshell* out);
 /* MatMult_KronSumShell(A, x, y): src/DMRGKron.cpp:1827-1869.  Device pointers, length NumStates(). */
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y);
 /* profiling aids: run only stage 1 (V = A·X panels) or stage 2 (Y = Σ V·Bᵀ) of an apply, and their useful flops */
