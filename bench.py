@@ -260,6 +260,19 @@ def main():
     achieved = (f1 + f2) / ((t1 + t2) * 1e-3) / 1e12
     peaks, peaks_kind = measured_peaks()
 
+    # the eigen-solve around the matvec (EPSSolve call site): time per Lanczos iteration = matvec + orthogonalisation
+    lz = {}
+    try:
+        H.EPSSolve(tol=1e-30, ncv=16, max_it=1)
+        ev[0].record()
+        _, _, stl = H.EPSSolve(tol=1e-30, ncv=16, max_it=3)
+        ev[1].record()
+        torch.cuda.synchronize()
+        lz = {"ms_per_iteration": ev[0].elapsed_time(ev[1]) / max(1, stl["nmatvec"]), "nmatvec": stl["nmatvec"], "ncv": 16,
+              "matvec_share": ms_step / (ev[0].elapsed_time(ev[1]) / max(1, stl["nmatvec"]))}
+    except Exception as exc:
+        lz = {"error": repr(exc)}
+
     # e2e: the reference-facing call with HOST buffers, copies inside the timed region
     hx = torch.from_numpy(wl.random_state(2)).pin_memory()
     hy = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -293,6 +306,7 @@ def main():
                      "peak_source": "cuBLAS DGEMM %d^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)" % 6144,
                      "stage_ms": [t1, t2], "stage_flops": [f1, f2],
                      "hbm_frac_of_%s_peak" % peaks_kind: (st["alg_bytes"] / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"]},
+        "lanczos": lz,
         "alg": {"bytes_per_apply": st["alg_bytes"], "flops_per_apply": st["alg_flops"], "D": n,
                 "tiles": [st["tiles_stage1"], st["tiles_stage2"]]},
     }

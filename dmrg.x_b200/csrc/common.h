@@ -158,6 +158,15 @@ struct XForm {
     int nstates_old = 0;
 };
 
+/* DMRGX_TRACE=1: wall-clock of the sub-phases of the host-side orchestration (device drained at each mark), to stderr */
+struct Trace {
+    Ctx* ctx; const char* what; double t0; bool on;
+    static bool enabled();
+    static double now();
+    Trace(Ctx* c, const char* w);
+    void mark(const char* label);
+};
+
 /* ---- functions implemented across the .cpp files ---- */
 Block* block_from_csr_begin(Ctx*, int nsites, const std::vector<double>& qn, const std::vector<long long>& sizes);
 void block_set_operator(Block*, int optype, int isite, const long long* rowptr, const long long* col, const double* val);

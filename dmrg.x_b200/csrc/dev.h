@@ -113,6 +113,11 @@ void scal(Stream*, double* x, long long n, double a);
 /* dense symmetric eigendecomposition of an n×n block (in place): on exit row k of A (row-major) is the
    k-th eigenvector, eigenvalues ascending in d_w */
 int syevd(Stream*, int n, double* d_A, double* d_w);
+/* the same for a batch of independent blocks: block b is n[b]×n[b] at d_A[b], eigenvalues to d_w[b].  The blocks are
+   spread over a pool of solver streams (largest first) so that small and medium blocks, which cannot fill 148 SMs
+   one at a time, run concurrently; ordered after everything queued on the main stream, and the main stream
+   continues only when all blocks are done.  Returns 0 or the first failure. */
+int syevd_batch(Stream*, int nblocks, const int* n, double* const* d_A, double* const* d_w);
 /* dst[k][:] = src[(n-1-k)][:], k < m   (the m largest eigenvectors, descending) */
 void gather_rows_reversed(Stream*, const double* src, int n, int m, double* dst);
 /* |x_i| < tol -> 0 */

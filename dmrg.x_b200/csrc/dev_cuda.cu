@@ -12,9 +12,13 @@
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
+#include <atomic>
+#include <map>
+#include <unordered_map>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,7 +54,22 @@ struct Stream {
     void* solver_work = nullptr;
     size_t solver_work_bytes = 0;
     int num_sms = 148;
+    /* pool of solver lanes for syevd_batch: one stream + cuSOLVER handle + workspace each */
+    struct Lane {
+        cudaStream_t s = nullptr;
+        cusolverDnHandle_t h = nullptr;
+        void* work = nullptr;
+        size_t work_bytes = 0;
+        int* info = nullptr;
+    };
+    std::vector<Lane> lanes;
+    std::map<size_t, std::vector<void*>> free_lists; /* caching allocator: size class -> free blocks */
+    std::unordered_map<void*, size_t> live;
+    size_t bytes_reserved = 0;
+    cudaEvent_t ev_main = nullptr;
+    std::vector<cudaEvent_t> ev_lane;
 };
+constexpr int SOLVER_LANES = 8;
 
 constexpr int RED_BLOCKS = 592; /* 148 SMs × 4 resident CTAs */
 constexpr int RED_MAXVEC = 40;
@@ -71,10 +90,6 @@ int init(int device, void* user_stream, Stream** out) {
         cudaDeviceProp prop;
         CUDA_OK(cudaGetDeviceProperties(&prop, device));
         st->num_sms = prop.multiProcessorCount;
-        cudaMemPool_t pool;
-        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long thr = ~0ULL;
-        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         CUDA_OK(cudaMalloc(&st->partials, sizeof(double) * RED_BLOCKS * RED_MAXVEC));
         CUDA_OK(cudaMalloc(&st->info, sizeof(int) * 4));
         if (cusolverDnCreate(&st->solver) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
@@ -90,6 +105,16 @@ void destroy(Stream* st) {
     cudaStreamSynchronize(st->s);
     if (st->solver) cusolverDnDestroy(st->solver);
     if (st->solver_work) cudaFree(st->solver_work);
+    for (auto& l : st->lanes) {
+        if (l.h) cusolverDnDestroy(l.h);
+        if (l.work) cudaFree(l.work);
+        if (l.info) cudaFree(l.info);
+        if (l.s) cudaStreamDestroy(l.s);
+    }
+    for (auto& e : st->ev_lane) cudaEventDestroy(e);
+    if (st->ev_main) cudaEventDestroy(st->ev_main);
+    for (auto& kv : st->free_lists) for (void* q : kv.second) cudaFree(q);
+    for (auto& kv : st->live) cudaFree(kv.first);
     cudaFree(st->partials);
     cudaFree(st->info);
     if (st->own) cudaStreamDestroy(st->s);
@@ -98,13 +123,46 @@ void destroy(Stream* st) {
 int device_of(Stream* st) { return st->device; }
 void* raw_stream(Stream* st) { return (void*)st->s; }
 
+/* Caching allocator.  A DMRG sweep frees and allocates panels of slowly varying sizes every step; handing each one
+   back to the driver (cudaFreeAsync) let the pool fragment and re-map, which showed up as 200-700 ms stalls inside single
+   steps.  Blocks are rounded up to one of four geometric size classes per octave and kept on per-class free lists for
+   the life of the context.  Everything is ordered on the one stream of the context, so a freed block can be handed out
+   again immediately: its new user is queued behind its old one. */
+static size_t size_class(size_t bytes) {
+    if (bytes <= 512) return 512;
+    size_t p = 512;
+    while (p * 2 <= bytes) p *= 2;            /* p <= bytes < 2p */
+    const size_t q = p / 4;
+    return p + ((bytes - p + q - 1) / q) * q;  /* p, 1.25p, 1.5p, 1.75p, 2p */
+}
 void* malloc_bytes(Stream* st, size_t bytes) {
+    const size_t cls = size_class(bytes);
+    auto f = st->free_lists.find(cls);
+    if (f != st->free_lists.end() && !f->second.empty()) {
+        void* p = f->second.back();
+        f->second.pop_back();
+        st->live[p] = cls;
+        return p;
+    }
     void* p = nullptr;
-    if (bytes == 0) bytes = 8;
-    CUDA_OK(cudaMallocAsync(&p, bytes, st->s));
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) { /* out of memory: give the cached blocks back and retry once */
+        cudaGetLastError();
+        cudaStreamSynchronize(st->s);
+        for (auto& kv : st->free_lists) { for (void* q : kv.second) cudaFree(q); kv.second.clear(); }
+        CUDA_OK(cudaMalloc(&p, cls));
+    }
+    st->live[p] = cls;
+    st->bytes_reserved += cls;
     return p;
 }
-void free_bytes(Stream* st, void* p) { if (p) cudaFreeAsync(p, st->s); }
+void free_bytes(Stream* st, void* p) {
+    if (!p) return;
+    auto f = st->live.find(p);
+    if (f == st->live.end()) return;
+    st->free_lists[f->second].push_back(p);
+    st->live.erase(f);
+}
 void* malloc_pinned(size_t bytes) { void* p = nullptr; CUDA_OK(cudaMallocHost(&p, bytes ? bytes : 8)); return p; }
 void free_pinned(void* p) { if (p) cudaFreeHost(p); }
 void h2d(Stream* st, void* dst, const void* src, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st->s)); }
@@ -575,6 +633,75 @@ int syevd(Stream* st, int n, double* d_A, double* d_w) {
     CUDA_OK(cudaMemcpyAsync(&info, st->info, sizeof(int), cudaMemcpyDeviceToHost, st->s));
     CUDA_OK(cudaStreamSynchronize(st->s));
     if (info != 0) { g_err = "cusolverDnDsyevd: info != 0"; return 104; }
+    return 0;
+}
+
+/* One worker thread per lane pulls blocks (largest first) from a shared counter: cuSOLVER's syevd synchronises with the
+   host internally, so concurrency across blocks needs concurrent host callers as well as separate streams. */
+int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, double* const* d_w) {
+    if (nblocks <= 0) return 0;
+    if (st->lanes.empty()) {
+        st->lanes.resize(SOLVER_LANES);
+        st->ev_lane.resize(SOLVER_LANES);
+        CUDA_OK(cudaEventCreateWithFlags(&st->ev_main, cudaEventDisableTiming));
+        for (int i = 0; i < SOLVER_LANES; ++i) {
+            Stream::Lane& l = st->lanes[i];
+            CUDA_OK(cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking));
+            if (cusolverDnCreate(&l.h) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
+            cusolverDnSetStream(l.h, l.s);
+            CUDA_OK(cudaMalloc(&l.info, sizeof(int)));
+            CUDA_OK(cudaEventCreateWithFlags(&st->ev_lane[i], cudaEventDisableTiming));
+        }
+    }
+    std::vector<int> order;
+    for (int b = 0; b < nblocks; ++b) if (n[b] > 0) order.push_back(b);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
+    const int nl = (int)std::min<size_t>(st->lanes.size(), order.size());
+    if (nl == 0) return 0;
+    CUDA_OK(cudaEventRecord(st->ev_main, st->s));
+    for (int i = 0; i < nl; ++i) CUDA_OK(cudaStreamWaitEvent(st->lanes[i].s, st->ev_main, 0));
+    std::atomic<int> next(0), fail(0);
+    std::string errs[SOLVER_LANES];
+    auto worker = [&](int li) {
+        cudaSetDevice(st->device);
+        Stream::Lane& l = st->lanes[li];
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= (int)order.size() || fail.load()) break;
+            const int b = order[k], nb = n[b];
+            int lwork = 0;
+            if (cusolverDnDsyevd_bufferSize(l.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, d_A[b], nb, d_w[b], &lwork) !=
+                CUSOLVER_STATUS_SUCCESS) { errs[li] = "cusolverDnDsyevd_bufferSize failed"; fail = 102; break; }
+            const size_t need = sizeof(double) * (size_t)lwork;
+            if (need > l.work_bytes) {
+                cudaStreamSynchronize(l.s);
+                if (l.work) cudaFree(l.work);
+                /* grow geometrically (cudaFree synchronises the whole device): sizes creep up step by step in a sweep */
+                const size_t grow = std::max<size_t>(2 * need, (size_t)64 << 20);
+                if (cudaMalloc(&l.work, grow) != cudaSuccess) { errs[li] = "cudaMalloc of the eigensolver workspace failed"; fail = 105; break; }
+                l.work_bytes = grow;
+            }
+            if (cusolverDnDsyevd(l.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, d_A[b], nb, d_w[b], (double*)l.work, lwork,
+                                 l.info) != CUSOLVER_STATUS_SUCCESS) { errs[li] = "cusolverDnDsyevd failed"; fail = 103; break; }
+            int info = 0;
+            if (cudaMemcpyAsync(&info, l.info, sizeof(int), cudaMemcpyDeviceToHost, l.s) != cudaSuccess ||
+                cudaStreamSynchronize(l.s) != cudaSuccess) { errs[li] = "eigensolver lane: CUDA error"; fail = 106; break; }
+            if (info != 0) { errs[li] = "cusolverDnDsyevd: info != 0"; fail = 104; break; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nl; ++i) th.emplace_back(worker, i);
+    worker(0);
+    for (auto& t : th) t.join();
+    g_launches += (long long)order.size();
+    for (int i = 0; i < nl; ++i) {
+        CUDA_OK(cudaEventRecord(st->ev_lane[i], st->lanes[i].s));
+        CUDA_OK(cudaStreamWaitEvent(st->s, st->ev_lane[i], 0));
+    }
+    if (fail.load()) {
+        for (auto& e : errs) if (!e.empty()) { g_err = e; break; }
+        return fail.load();
+    }
     return 0;
 }
 

@@ -67,6 +67,7 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     std::vector<double> hh(2 * (ld + 1) + 1);
     std::vector<double> T((size_t)ld * ld, 0.0);
 
+    Trace tr(ctx, "eigs");
     dev::fill_random(st, V, N, opts.seed);
     dev::dot(st, V, V, N, d_nrm2);
     dev::scale_inv_norm(st, V, d_nrm2, V, N);
@@ -127,6 +128,7 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     dev::dot(st, V, V, N, d_nrm2);
     dev::scale_inv_norm(st, V, d_nrm2, d_psi, N);
     dev::sync(st);
+    tr.mark("solve");
     stats.resid = resid;
     if (stats_out) *stats_out = stats;
     return theta;

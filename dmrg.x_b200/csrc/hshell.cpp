@@ -67,6 +67,7 @@ inline bool contiguous_dense(const Tile& t) {
 
 static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, int nterms) {
     Ctx* ctx = kron->ctx;
+    Trace tr(ctx, "build_shell");
     std::unique_ptr<HShell> H(new HShell());
     H->ctx = ctx; H->kron = kron; H->n = kron->nstates(); H->nterms = nterms;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
@@ -141,6 +142,7 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
         }
     }
 
+    tr.mark("presum");
     /* ---- stage 1: V panels;  stage 2: Y panels ---- */
     std::vector<std::vector<Contribution>> ycontrib(np);
     for (size_t g = 0; g < groups.size(); ++g) {
@@ -219,8 +221,10 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
         const int nLp = SL.size[kron->pairs[p].il], nRp = SR.size[kron->pairs[p].ir];
         emit_cells(H->stage2, yoff(kron->off[p]), true, nRp, nLp, nRp, ycontrib[p], true);
     }
+    tr.mark("plan");
     H->stage1.upload(ctx);
     H->stage2.upload(ctx);
+    tr.mark("upload");
     H->alg_bytes = 16LL * H->n + tile_bytes;
     H->alg_flops = H->stage1.flops + H->stage2.flops;
     return H.release();

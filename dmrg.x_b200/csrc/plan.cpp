@@ -6,12 +6,26 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
 #include "plan.h"
 
 namespace dmrgx {
+
+bool Trace::enabled() { static const bool on = getenv("DMRGX_TRACE") != nullptr; return on; }
+double Trace::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+Trace::Trace(Ctx* c, const char* w) : ctx(c), what(w), t0(0), on(enabled()) { if (on) { dev::sync(ctx->st); t0 = now(); } }
+void Trace::mark(const char* label) {
+    if (!on) return;
+    dev::sync(ctx->st);
+    const double t = now();
+    fprintf(stderr, "[trace] %s.%s %.3f ms\n", what, label, (t - t0) * 1e3);
+    t0 = t;
+}
 
 void Plan::upload(Ctx* ctx) {
     if (items.empty()) return;

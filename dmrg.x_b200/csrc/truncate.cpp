@@ -24,29 +24,37 @@ namespace {
 struct Eigen_t { double eigval; int seqIdx, epsIdx, blkIdx; };
 }
 
-static XForm* truncate_side(const Kron* kron, const double* d_psi, long long mstates, bool left) {
+/* one side (left or right) of GetTruncation, in two phases so that the eigendecompositions of BOTH sides go out as
+   one batch over the solver lanes */
+struct SideJob {
+    bool left;
+    std::vector<long long> roff, woff;
+    std::vector<int> dim, blkidx;
+    long long wtot = 0;
+    BufRef rho, dw;
+};
+
+static void side_build_rho(const Kron* kron, const double* d_psi, bool left, SideJob& J) {
     Ctx* ctx = kron->ctx;
-    dev::Stream* st = ctx->st;
-    const Block* blk = left ? kron->L : kron->R;
-    const Sectors& S = blk->sec;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     const int np = (int)kron->pairs.size();
+    J.left = left;
     /* ---- ρ blocks, one per sector pair, in KronBlocks order (:1709-1775) ---- */
-    std::vector<long long> roff(np + 1, 0);
-    std::vector<int> dim(np), blkidx(np);
+    J.roff.assign(np + 1, 0); J.woff.assign(np + 1, 0);
+    J.dim.resize(np); J.blkidx.resize(np);
     for (int p = 0; p < np; ++p) {
-        dim[p] = left ? SL.size[kron->pairs[p].il] : SR.size[kron->pairs[p].ir];
-        blkidx[p] = left ? kron->pairs[p].il : kron->pairs[p].ir;
-        roff[p + 1] = roff[p] + (long long)dim[p] * dim[p];
+        J.dim[p] = left ? SL.size[kron->pairs[p].il] : SR.size[kron->pairs[p].ir];
+        J.blkidx[p] = left ? kron->pairs[p].il : kron->pairs[p].ir;
+        J.roff[p + 1] = J.roff[p] + (long long)J.dim[p] * J.dim[p];
+        J.woff[p + 1] = J.woff[p] + J.dim[p];
     }
-    long long wtot = 0;
-    for (int p = 0; p < np; ++p) wtot += dim[p];
-    BufRef rho = std::make_shared<DevBuf>(ctx, std::max<long long>(1, roff.back()) * 8);
-    BufRef dw = std::make_shared<DevBuf>(ctx, std::max<long long>(1, wtot) * 8);
+    J.wtot = J.woff[np];
+    J.rho = std::make_shared<DevBuf>(ctx, std::max<long long>(1, J.roff.back()) * 8);
+    J.dw = std::make_shared<DevBuf>(ctx, std::max<long long>(1, J.wtot) * 8);
     Plan plan;
     for (int p = 0; p < np; ++p) {
         const int nL = SL.size[kron->pairs[p].il], nR = SR.size[kron->pairs[p].ir];
-        const int n = dim[p];
+        const int n = J.dim[p];
         if (n == 0) continue;
         Contribution c;
         c.r0 = 0; c.c0 = 0; c.nr = n; c.nc = n;
@@ -61,18 +69,24 @@ static XForm* truncate_side(const Kron* kron, const double* d_psi, long long mst
         }
         if (c.seg.K == 0) continue;
         std::vector<Contribution> cs = {c};
-        emit_cells(plan, rho->as<double>() + roff[p], false, n, n, n, cs, true);
+        emit_cells(plan, J.rho->as<double>() + J.roff[p], false, n, n, n, cs, true);
     }
     plan.upload(ctx);
     plan.run(ctx, d_psi, nullptr);
-    /* ---- full spectrum of every block (EPSLAPACK, all n pairs, :1976-1994) ---- */
-    std::vector<long long> woff(np + 1, 0);
-    for (int p = 0; p < np; ++p) woff[p + 1] = woff[p] + dim[p];
-    for (int p = 0; p < np; ++p) {
-        if (dim[p] == 0) continue;
-        int e = dev::syevd(st, dim[p], rho->as<double>() + roff[p], dw->as<double>() + woff[p]);
-        if (e) throw Err(ERR_GENERIC, std::string("eigendecomposition of a reduced density matrix block failed: ") + dev::last_error());
-    }
+    dev::sync(ctx->st); /* the plan's device lists die with this scope */
+}
+
+static XForm* side_select(const Kron* kron, long long mstates, const SideJob& J) {
+    Ctx* ctx = kron->ctx;
+    dev::Stream* st = ctx->st;
+    const bool left = J.left;
+    const Block* blk = left ? kron->L : kron->R;
+    const Sectors& S = blk->sec;
+    const int np = (int)kron->pairs.size();
+    const std::vector<long long>&roff = J.roff, &woff = J.woff;
+    const std::vector<int>&dim = J.dim, &blkidx = J.blkidx;
+    const long long wtot = J.wtot;
+    const BufRef &rho = J.rho, &dw = J.dw;
     std::vector<double> w(std::max<long long>(1, wtot));
     dev::d2h(st, w.data(), dw->p, (size_t)wtot * 8);
     dev::sync(st);
@@ -122,8 +136,27 @@ static XForm* truncate_side(const Kron* kron, const double* d_psi, long long mst
 }
 
 void truncate(const Kron* kron, const double* d_psi, long long mstates, XForm** L, XForm** R) {
-    std::unique_ptr<XForm> l(truncate_side(kron, d_psi, mstates, true));
-    std::unique_ptr<XForm> r(truncate_side(kron, d_psi, mstates, false));
+    Trace tr(kron->ctx, "truncate");
+    SideJob JL, JR;
+    side_build_rho(kron, d_psi, true, JL);
+    side_build_rho(kron, d_psi, false, JR);
+    tr.mark("rho");
+    /* ---- full spectrum of every block of both sides (EPSLAPACK, all n pairs, :1976-1994) ---- */
+    std::vector<int> n;
+    std::vector<double*> A, W;
+    for (SideJob* J : {&JL, &JR})
+        for (size_t p = 0; p < J->dim.size(); ++p) {
+            if (J->dim[p] == 0) continue;
+            n.push_back(J->dim[p]);
+            A.push_back(J->rho->as<double>() + J->roff[p]);
+            W.push_back(J->dw->as<double>() + J->woff[p]);
+        }
+    const int e = dev::syevd_batch(kron->ctx->st, (int)n.size(), n.data(), A.data(), W.data());
+    if (e) throw Err(ERR_GENERIC, std::string("eigendecomposition of a reduced density matrix block failed: ") + dev::last_error());
+    tr.mark("syevd_batch");
+    std::unique_ptr<XForm> l(side_select(kron, mstates, JL));
+    std::unique_ptr<XForm> r(side_select(kron, mstates, JR));
+    tr.mark("select");
     *L = l.release();
     *R = r.release();
 }
@@ -131,6 +164,7 @@ void truncate(const Kron* kron, const double* d_psi, long long mstates, XForm** 
 /* src/DMRGBlock.cpp:677-823 */
 Block* rotate(const Block* enl, const XForm* xf) {
     Ctx* ctx = enl->ctx;
+    Trace tr(ctx, "rotate");
     const Sectors& SO = enl->sec;
     if (xf->nstates_old != SO.nstates()) throw Err(ERR_GENERIC, "RotMatT_in incorrect number of cols.");
     const Sectors& SN = xf->newsec;
@@ -162,8 +196,10 @@ Block* rotate(const Block* enl, const XForm* xf) {
             otot += (long long)SN.size[Ip] * SN.size[Jp];
         }
     }
+    tr.mark("setup");
     BufRef tbuf = std::make_shared<DevBuf>(ctx, std::max<long long>(1, ttot) * 8);
     BufRef obuf = std::make_shared<DevBuf>(ctx, std::max<long long>(1, otot) * 8);
+    tr.mark("alloc");
     Plan p1, p2;
     for (const Blk& b : blks) {
         const Operator& O = *jobs[b.job].src;
@@ -204,10 +240,14 @@ Block* rotate(const Block* enl, const XForm* xf) {
         jobs[b.job].dst->tiles[b.Ip].push_back(o);
     }
     for (Job& j : jobs) { j.dst->shift = j.src->shift; j.dst->present = true; }
+    tr.mark("plan");
     p1.upload(ctx);
     p2.upload(ctx);
+    tr.mark("upload");
     p1.run(ctx);
+    tr.mark("run1");
     p2.run(ctx);
+    tr.mark("run2");
     /* Sm' = (Sp')ᵀ as views (the reference rebuilds Sm on demand, src/DMRGBlock.cpp:623-636) */
     for (int i = 0; i < out->nsites; ++i) {
         Operator& sm = out->Sm[i];

@@ -174,4 +174,10 @@ int syevd(Stream*, int n, double* A, double* w) {
     return 0;
 }
 
+int syevd_batch(Stream* st, int nblocks, const int* n, double* const* A, double* const* w) {
+    for (int b = 0; b < nblocks; ++b)
+        if (n[b] > 0) { int e = syevd(st, n[b], A[b], w[b]); if (e) return e; }
+    return 0;
+}
+
 }  // namespace dev
