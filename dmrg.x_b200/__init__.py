@@ -105,14 +105,27 @@ def HamiltonianTerms(Lx, Ly, J1=1.0, Jz1=0.0, J2=1.0, Jz2=0.0, nsites=-1, bcx=0,
     return [(float(a[i]), int(iop[i]), int(isite[i]), int(jop[i]), int(jsite[i])) for i in range(k)]
 
 
-class Context:
-    """One CUDA device + stream (stands in for the MPI communicator of the reference objects)."""
+def dist_unique_id():
+    """128-byte communicator id (an ncclUniqueId): rank 0 creates it, the launcher broadcasts it (dmrgx_dist_unique_id)."""
+    buf = C.create_string_buffer(128)
+    _chk(lib().dmrgx_dist_unique_id(buf))
+    return buf.raw
 
-    def __init__(self, device=0, stream=None):
+
+class Context:
+    """One CUDA device + stream (stands in for the MPI communicator of the reference objects).  With world > 1 this is
+    one rank of a multi-GPU job (one process per GPU): objects created on it are sharded by superblock row ranges."""
+
+    def __init__(self, device=0, stream=None, rank=0, world=1, unique_id=None):
         h = C.c_void_p()
-        _chk(lib().dmrgx_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(h)))
+        if world > 1:
+            assert unique_id is not None and len(unique_id) == 128
+            _chk(lib().dmrgx_ctx_create_dist(int(device), C.c_void_p(stream or 0), int(rank), int(world), C.c_char_p(unique_id), C.byref(h)))
+        else:
+            _chk(lib().dmrgx_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(h)))
         self.h = h
         self.device = device
+        self.rank, self.world = rank, world
 
     def sync(self):
         _chk(lib().dmrgx_ctx_sync(self.h))
@@ -307,6 +320,18 @@ class HShell:
         yp = y.ptr if isinstance(y, DeviceVector) else C.c_void_p(int(y))
         _chk(lib().dmrgx_hshell_apply(self.h, xp, yp))
 
+    def row_range(self):
+        """(begin, end, cuts): superblock rows this rank owns and the ownership table of all ranks"""
+        b, e = LL(), LL()
+        cuts = np.zeros(self.ctx.world + 1, np.int64)
+        _chk(lib().dmrgx_hshell_row_range(self.h, C.byref(b), C.byref(e), _p(cuts)))
+        return b.value, e.value, cuts
+
+    def MatMult_sharded(self, x, y):
+        """distributed MatMult: x holds this rank's rows on entry (full-length buffer), is all-gathered in place, then this
+        rank's rows of y are computed"""
+        _chk(lib().dmrgx_hshell_apply_sharded(self.h, x.ptr, y.ptr))
+
     def MatMult_stage(self, stage, x, y):
         _chk(lib().dmrgx_hshell_apply_stage(self.h, int(stage), x.ptr, y.ptr))
 
@@ -316,10 +341,12 @@ class HShell:
         return a.value, b.value
 
     def MatMult_host(self, x, y=None):
-        """The PETSc-callback shape: host arrays in and out (H2D + kernels + D2H inside)."""
+        """The PETSc-callback shape: host arrays in and out (H2D + kernels + D2H inside).  On a multi-GPU context x and y
+        are this rank's local rows (VecGetArray of an MPI Vec)."""
         x = _d(x)
         if y is None:
-            y = np.zeros(self.n)
+            b, e, _ = self.row_range()
+            y = np.zeros(e - b)
         _chk(lib().dmrgx_hshell_apply_host(self.h, _p(x), _p(y)))
         return y
 

@@ -44,6 +44,22 @@ int dmrgx_ctx_create(int device, void* stream, dmrgx_ctx* out) {
     *out = (dmrgx_ctx)c;
     return 0;
 }
+int dmrgx_dist_unique_id(void* out128) {
+    int e = dev::comm_unique_id(out128);
+    if (e) g_msg = dev::last_error();
+    return e;
+}
+int dmrgx_ctx_create_dist(int device, void* stream, int rank, int world, const void* id128, dmrgx_ctx* out) {
+    if (world < 1 || rank < 0 || rank >= world) { g_msg = "dmrgx_ctx_create_dist: bad rank / world"; *out = nullptr; return ERR_ARG_OUTOFRANGE; }
+    int e = dmrgx_ctx_create(device, stream, out);
+    if (e) return e;
+    Ctx* c = C(*out);
+    e = dev::comm_init(c->st, rank, world, id128);
+    if (e) { g_msg = dev::last_error(); dmrgx_ctx_destroy(*out); *out = nullptr; return e; }
+    c->rank = rank; c->world = world;
+    return 0;
+}
+int dmrgx_ctx_rank(dmrgx_ctx ctx, int* rank, int* world) { *rank = C(ctx)->rank; *world = C(ctx)->world; return 0; }
 int dmrgx_ctx_destroy(dmrgx_ctx ctx) { if (!ctx) return 0; return guard([&] { dev::destroy(C(ctx)->st); delete C(ctx); }); }
 int dmrgx_ctx_sync(dmrgx_ctx ctx) { return guard([&] { dev::sync(C(ctx)->st); }); }
 int dmrgx_ctx_set_dense_threshold(dmrgx_ctx ctx, double fill) { C(ctx)->dense_fill_threshold = fill; return 0; }
@@ -127,6 +143,14 @@ int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, cons
     });
 }
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y) { return guard([&] { hshell_apply(H(h), d_x, d_y); }); }
+int dmrgx_hshell_apply_sharded(dmrgx_hshell h, double* d_x, double* d_y) { return guard([&] { hshell_apply_sharded(H(h), d_x, d_y); }); }
+int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmrgx_int* cuts) {
+    HShell* s = H(h);
+    if (begin) *begin = s->row_begin;
+    if (end) *end = s->row_end;
+    if (cuts) for (size_t i = 0; i < s->row_cuts.size(); ++i) cuts[i] = s->row_cuts[i];
+    return 0;
+}
 int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y) {
     return guard([&] {
         HShell* s = H(h);
@@ -148,9 +172,11 @@ int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
             s->xbuf = std::make_shared<DevBuf>(ctx, bytes);
             s->ybuf = std::make_shared<DevBuf>(ctx, bytes);
         }
-        dev::h2d(ctx->st, s->xbuf->p, x, bytes);
-        hshell_apply(s, s->xbuf->as<double>(), s->ybuf->as<double>());
-        dev::d2h(ctx->st, y, s->ybuf->p, bytes);
+        /* x / y are this rank's LOCAL rows (what VecGetArray gives on the reference's MPI vectors); the whole vector on one GPU */
+        const size_t lbytes = (size_t)(s->row_end - s->row_begin) * 8;
+        dev::h2d(ctx->st, s->xbuf->as<double>() + s->row_begin, x, lbytes);
+        hshell_apply_sharded(s, s->xbuf->as<double>(), s->ybuf->as<double>());
+        dev::d2h(ctx->st, y, s->ybuf->as<double>() + s->row_begin, lbytes);
         dev::sync(ctx->st);
     });
 }
@@ -232,9 +258,10 @@ int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value) {
         HShell* s = H(h1);
         Ctx* ctx = s->ctx;
         BufRef y = std::make_shared<DevBuf>(ctx, (size_t)s->n * 8 + 8);
-        hshell_apply(s, d_psi, y->as<double>());
+        hshell_apply(s, d_psi, y->as<double>()); /* psi is complete on every rank; each computes its own rows */
         double* d_out = y->as<double>() + s->n;
-        dev::dot(ctx->st, d_psi, y->as<double>(), s->n, d_out);
+        dev::dot(ctx->st, d_psi + s->row_begin, y->as<double>() + s->row_begin, s->row_end - s->row_begin, d_out);
+        dev::allreduce_sum(ctx->st, d_out, 1);
         dev::d2h(ctx->st, value, d_out, 8);
         dev::sync(ctx->st);
     });

@@ -134,6 +134,9 @@ struct HShell {
     Ctx* ctx = nullptr;
     const Kron* kron = nullptr;
     long long n = 0;
+    /* superblock rows this rank computes ([0,n) on one GPU) and the ownership table of all ranks (world+1 entries) */
+    long long row_begin = 0, row_end = 0;
+    std::vector<long long> row_cuts;
     Plan stage1, stage2;
     BufRef work;                 /* V panels of stage 1 */
     BufRef xbuf, ybuf;           /* device staging of the host-buffer entry point */
@@ -184,6 +187,7 @@ HShell* hshell_create(const Kron*, const std::vector<Term>& terms);
 HShell* hshell_create_single(const Kron*, int opl, int il, int opr, int ir);
 HShell* hshell_create_product(const Kron*, const std::vector<std::pair<int, int>>& lops, const std::vector<std::pair<int, int>>& rops);
 void hshell_apply(HShell*, const double* d_x, double* d_y);
+void hshell_apply_sharded(HShell*, double* d_x, double* d_y);
 
 struct EigsOpts { double tol = 1e-8; int ncv = 16; int max_it = 0; unsigned long long seed = 20261018ULL; };
 struct EigsStats { long long nmatvec = 0, nrestart = 0; double resid = 0; int converged = 0; };

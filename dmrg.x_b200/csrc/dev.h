@@ -77,6 +77,21 @@ void sync(Stream*);
 /* number of kernel launches issued through this layer so far (bench.py's gpu_launches) */
 long long launch_count();
 
+/* ---- collectives: one process per GPU, NCCL over NVLink/NVSwitch.  The path has exactly three exchange
+   steps: the all-gather of the sharded superblock vector before an apply, the all-reduce of a handful of scalars per
+   Lanczos step, and broadcasts of eigenvector / rotated-operator panels from the rank that computed them.  All calls
+   are enqueued on the context's stream (device-ordered, no host synchronisation). ---- */
+constexpr int COMM_ID_BYTES = 128;                       /* ncclUniqueId */
+int comm_unique_id(void* out);                           /* rank 0 creates it, the launcher hands it to the others */
+int comm_init(Stream*, int rank, int world, const void* id);
+int comm_rank(Stream*);
+int comm_world(Stream*);
+void allreduce_sum(Stream*, double* d_buf, long long n); /* in place */
+/* in place: rank r owns d_buf[offsets[r] .. offsets[r+1]) and receives all other ranges */
+void allgatherv(Stream*, double* d_buf, const long long* offsets);
+/* a batch of broadcasts, root[i] sends d_ptr[i][0..count[i]) to everybody (one NCCL group) */
+void bcast_batch(Stream*, int n, double* const* d_ptr, const long long* count, const int* root);
+
 /* chain contraction engine */
 /* x / y: base pointers that offset-typed operands (SEGF_*_X, c_in_y) are relative to, so one plan serves any
    pair of device vectors (the Lanczos basis vectors change every step; the plan does not). */
@@ -97,7 +112,8 @@ struct ReduceItem {
 void run_reduce(Stream*, const ReduceItem* d_items, int nitems, double* y, const double* w);
 
 /* vector kernels of the thick-restart Lanczos (all results stay on the device) */
-void fill_random(Stream*, double* x, long long n, unsigned long long seed);
+/* x[i] = u(seed, first + i): depends on the GLOBAL index only */
+void fill_random(Stream*, double* x, long long n, unsigned long long seed, long long first = 0);
 void multidot(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, double* d_out);
 /* w -= Σ_i d_coef[i] V_i ; if d_dots2: d_dots2[i] = V_i·w_new (fused second Gram-Schmidt pass);
    if d_nrm2: *d_nrm2 = ||w_new||²  */

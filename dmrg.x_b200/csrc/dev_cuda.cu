@@ -11,6 +11,8 @@
  */
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <atomic>
 #include <map>
@@ -68,6 +70,8 @@ struct Stream {
     size_t bytes_reserved = 0;
     cudaEvent_t ev_main = nullptr;
     std::vector<cudaEvent_t> ev_lane;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
 };
 constexpr int SOLVER_LANES = 8;
 
@@ -99,6 +103,7 @@ int init(int device, void* user_stream, Stream** out) {
     } catch (const std::exception&) { return 100; }
 }
 
+static void comm_destroy_(Stream* st);
 void destroy(Stream* st) {
     if (!st) return;
     cudaSetDevice(st->device);
@@ -113,6 +118,7 @@ void destroy(Stream* st) {
     }
     for (auto& e : st->ev_lane) cudaEventDestroy(e);
     if (st->ev_main) cudaEventDestroy(st->ev_main);
+    if (st->comm) comm_destroy_(st);
     for (auto& kv : st->free_lists) for (void* q : kv.second) cudaFree(q);
     for (auto& kv : st->live) cudaFree(kv.first);
     cudaFree(st->partials);
@@ -443,13 +449,14 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
-__global__ void fill_random_kernel(double* x, long long n, unsigned long long seed) {
+__global__ void fill_random_kernel(double* x, long long n, unsigned long long seed, long long first) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        x[i] = (double)(splitmix64(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL) >> 11) / 9007199254740992.0 - 0.5;
+        x[i] = (double)(splitmix64(seed + (unsigned long long)(first + i) * 0x9E3779B97F4A7C15ULL) >> 11) / 9007199254740992.0 - 0.5;
 }
-void fill_random(Stream* st, double* x, long long n, unsigned long long seed) {
+void fill_random(Stream* st, double* x, long long n, unsigned long long seed, long long first) {
+    if (n <= 0) return;
     int blocks = (int)std::min<long long>((n + 255) / 256, RED_BLOCKS);
-    fill_random_kernel<<<blocks, 256, 0, st->s>>>(x, n, seed);
+    fill_random_kernel<<<blocks, 256, 0, st->s>>>(x, n, seed, first);
     LAUNCH_CHECK();
 }
 
@@ -634,6 +641,92 @@ int syevd(Stream* st, int n, double* d_A, double* d_w) {
     CUDA_OK(cudaStreamSynchronize(st->s));
     if (info != 0) { g_err = "cusolverDnDsyevd: info != 0"; return 104; }
     return 0;
+}
+
+/* ================================================================================================
+ *  Collectives: NCCL, bound lazily (dlopen) so that a single-GPU process never needs the library.  In a Python
+ *  process torch has already loaded its bundled libnccl.so.2 and dlopen returns that same copy.
+ * ============================================================================================== */
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_err = std::string("cannot load NCCL: ") + dlerror(); return api; }
+#define BIND(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name); if (!api.name) { g_err = "NCCL symbol nccl" #name " missing"; return api; }
+    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(AllReduce) BIND(Broadcast) BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+#undef BIND
+    api.ok = true;
+    return api;
+}
+}  // namespace
+#define NCCL_OK(call)                                                                                     \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) {                                                                          \
+            char buf_[512];                                                                               \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, nccl().GetErrorString(r_)); \
+            g_err = buf_;                                                                                 \
+            fprintf(stderr, "[dmrgx] %s\n", buf_);                                                        \
+            throw std::runtime_error(buf_);                                                               \
+        }                                                                                                 \
+    } while (0)
+
+static void comm_destroy_(Stream* st) { if (st->comm && nccl().ok) nccl().CommDestroy(st->comm); st->comm = nullptr; }
+int comm_unique_id(void* out) {
+    static_assert(sizeof(ncclUniqueId) == COMM_ID_BYTES, "ncclUniqueId size");
+    if (!nccl().ok) return 110;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) { g_err = "ncclGetUniqueId failed"; return 111; }
+    std::memcpy(out, &id, sizeof id);
+    return 0;
+}
+int comm_init(Stream* st, int rank, int world, const void* idbytes) {
+    if (world <= 1) { st->rank = 0; st->world = 1; return 0; }
+    if (!nccl().ok) return 110;
+    ncclUniqueId id;
+    std::memcpy(&id, idbytes, sizeof id);
+    cudaSetDevice(st->device);
+    ncclResult_t r = nccl().CommInitRank(&st->comm, world, id, rank);
+    if (r != ncclSuccess) { g_err = std::string("ncclCommInitRank failed: ") + nccl().GetErrorString(r); return 112; }
+    st->rank = rank; st->world = world;
+    return 0;
+}
+int comm_rank(Stream* st) { return st->rank; }
+int comm_world(Stream* st) { return st->world; }
+void allreduce_sum(Stream* st, double* d_buf, long long n) {
+    if (st->world <= 1 || n <= 0) return;
+    NCCL_OK(nccl().AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, st->comm, st->s));
+}
+void allgatherv(Stream* st, double* d_buf, const long long* off) {
+    if (st->world <= 1) return;
+    NCCL_OK(nccl().GroupStart());
+    for (int r = 0; r < st->world; ++r) {
+        const long long cnt = off[r + 1] - off[r];
+        if (cnt > 0) NCCL_OK(nccl().Broadcast(d_buf + off[r], d_buf + off[r], (size_t)cnt, ncclDouble, r, st->comm, st->s));
+    }
+    NCCL_OK(nccl().GroupEnd());
+}
+void bcast_batch(Stream* st, int n, double* const* d_ptr, const long long* count, const int* root) {
+    if (st->world <= 1 || n <= 0) return;
+    NCCL_OK(nccl().GroupStart());
+    for (int i = 0; i < n; ++i)
+        if (count[i] > 0) NCCL_OK(nccl().Broadcast(d_ptr[i], d_ptr[i], (size_t)count[i], ncclDouble, root[i], st->comm, st->s));
+    NCCL_OK(nccl().GroupEnd());
 }
 
 /* One worker thread per lane pulls blocks (largest first) from a shared counter: cuSOLVER's syevd synchronises with the

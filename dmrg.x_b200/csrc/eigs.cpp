@@ -49,14 +49,21 @@ static void small_sym_eig(int n, std::vector<double> A, std::vector<double>& w, 
 double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* stats_out) {
     Ctx* ctx = H->ctx;
     dev::Stream* st = ctx->st;
-    const long long N = H->n;
+    /* Multi-GPU: every rank keeps only its own rows [R0, R0+N) of the Krylov basis; the matvec all-gathers the current
+       vector into a full-length buffer and every inner product is completed by an all-reduce of a few doubles.  All
+       ranks see identical reduced values, so they take identical decisions without further communication. */
+    const long long NG = H->n;                       /* global length */
+    const long long R0 = H->row_begin;
+    const long long N = H->row_end - H->row_begin;   /* local rows */
+    const bool dist = ctx->world > 1;
     EigsStats stats;
-    if (N <= 0) throw Err(ERR_GENERIC, "empty superblock");
-    const int ld = (int)std::max<long long>(1, std::min<long long>(opts.ncv < 2 ? 2 : opts.ncv, N));
+    if (NG <= 0) throw Err(ERR_GENERIC, "empty superblock");
+    const int ld = (int)std::max<long long>(1, std::min<long long>(opts.ncv < 2 ? 2 : opts.ncv, NG));
     /* SLEPc default max_it = max(100, 2N/ncv) restarts */
-    const long long max_it = opts.max_it > 0 ? opts.max_it : std::max<long long>(100, 2 * N / ld);
-    BufRef basis = std::make_shared<DevBuf>(ctx, (size_t)(ld + 1) * N * 8);
-    BufRef wbuf = std::make_shared<DevBuf>(ctx, (size_t)N * 8);
+    const long long max_it = opts.max_it > 0 ? opts.max_it : std::max<long long>(100, 2 * NG / ld);
+    BufRef basis = std::make_shared<DevBuf>(ctx, (size_t)(ld + 1) * std::max<long long>(1, N) * 8);
+    BufRef wbuf = std::make_shared<DevBuf>(ctx, (size_t)std::max<long long>(1, N) * 8);
+    BufRef xfull = dist ? std::make_shared<DevBuf>(ctx, (size_t)NG * 8) : nullptr;
     BufRef scal = std::make_shared<DevBuf>(ctx, (size_t)(2 * (ld + 2) + ld * ld) * 8);
     double* V = basis->as<double>();
     double* w = wbuf->as<double>();
@@ -68,8 +75,9 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     std::vector<double> T((size_t)ld * ld, 0.0);
 
     Trace tr(ctx, "eigs");
-    dev::fill_random(st, V, N, opts.seed);
+    dev::fill_random(st, V, N, opts.seed, R0); /* element i depends on (seed, global index) only: same start vector on any number of GPUs */
     dev::dot(st, V, V, N, d_nrm2);
+    dev::allreduce_sum(st, d_nrm2, 1);
     dev::scale_inv_norm(st, V, d_nrm2, V, N);
 
     int nc = ld, k = 0;
@@ -78,13 +86,21 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
         double beta_last = 0;
         bool invariant = false;
         for (int j = k; j < nc; ++j) {
-            hshell_apply(H, V + (size_t)j * N, w);
+            if (dist) {
+                dev::d2d(st, xfull->as<double>() + R0, V + (size_t)j * N, (size_t)N * 8);
+                hshell_apply_sharded(H, xfull->as<double>(), w - R0);
+            } else {
+                hshell_apply(H, V + (size_t)j * N, w);
+            }
             stats.nmatvec++;
             /* classical Gram-Schmidt against the whole basis, twice; coefficients never leave the device
                except as the ncv+2 numbers the projected matrix needs */
             dev::multidot(st, V, N, j + 1, w, N, d_h);
+            dev::allreduce_sum(st, d_h, j + 1);
             dev::multiaxpy(st, V, N, j + 1, d_h, w, N, d_h2, nullptr);
+            dev::allreduce_sum(st, d_h2, j + 1);
             dev::multiaxpy(st, V, N, j + 1, d_h2, w, N, nullptr, d_nrm2);
+            dev::allreduce_sum(st, d_nrm2, 1);
             dev::d2h(st, hh.data(), d_h, (size_t)(2 * (ld + 1) + 1) * 8);
             dev::sync(st);
             for (int i = 0; i <= j; ++i) {
@@ -126,7 +142,9 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     }
     /* normalise the Ritz vector (it is unit up to round-off) and hand it over */
     dev::dot(st, V, V, N, d_nrm2);
-    dev::scale_inv_norm(st, V, d_nrm2, d_psi, N);
+    dev::allreduce_sum(st, d_nrm2, 1);
+    dev::scale_inv_norm(st, V, d_nrm2, d_psi + R0, N);
+    if (dist) dev::allgatherv(st, d_psi, H->row_cuts.data()); /* psi complete on every rank (the truncation reads all of it) */
     dev::sync(st);
     tr.mark("solve");
     stats.resid = resid;

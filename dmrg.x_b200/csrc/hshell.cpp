@@ -12,6 +12,7 @@
  *  generate a product: they alias X or turn into an in-register AXPY.
  */
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <set>
 
@@ -65,13 +66,44 @@ inline bool contiguous_dense(const Tile& t) {
 }
 }  // namespace
 
-static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, int nterms) {
+/* sub-tile made of rows [lo,hi) (global block coordinates) of a tile; false if empty */
+static bool clip_tile_rows(Tile& t, int lo, int hi) {
+    const int a = std::max(lo, t.r0), b = std::min(hi, t.r0 + t.nr);
+    if (b <= a) return false;
+    const int d = a - t.r0;
+    if (t.fmt == T_DENSE) t.d += (long long)d * t.sr;
+    else if (t.fmt == T_CSR) t.rowptr += d;   /* row pointers are absolute offsets into col/val */
+    else { t.c0 += d; t.nc = b - a; }          /* a run of a scaled identity */
+    t.r0 = a; t.nr = b - a;
+    return true;
+}
+
+/* Builds the two-stage plan of the shell.  [row_begin,row_end) is the range of superblock rows this rank owns (cut at
+   left-row boundaries of the sector pairs; the whole vector on one GPU): only those rows of V and Y are planned, so the
+   ranks partition the work exactly, with no redundant products (the successor of KronSumShellSplitOwnership,
+   src/DMRGKron.cpp:1519-1704).  dry = cost model only: nothing is allocated, summed or uploaded; pair_cost receives the
+   useful flops per sector pair. */
+static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, int nterms, long long row_begin = 0, long long row_end = -1,
+                           bool dry = false, std::vector<double>* pair_cost = nullptr) {
     Ctx* ctx = kron->ctx;
-    Trace tr(ctx, "build_shell");
+    Trace tr(ctx, dry ? "build_shell(dry)" : "build_shell");
     std::unique_ptr<HShell> H(new HShell());
     H->ctx = ctx; H->kron = kron; H->n = kron->nstates(); H->nterms = nterms;
+    if (row_end < 0) row_end = H->n;
+    H->row_begin = row_begin; H->row_end = row_end;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     const int np = (int)kron->pairs.size();
+    /* owned left rows [lr0,lr1) of every pair */
+    std::vector<int> lr0(np, 0), lr1(np, 0);
+    for (int p = 0; p < np; ++p) {
+        const long long nR = SR.size[kron->pairs[p].ir];
+        if (nR == 0) continue;
+        const long long a = std::max(row_begin, kron->off[p]) - kron->off[p], b = std::min(row_end, kron->off[p + 1]) - kron->off[p];
+        if (b <= a) continue;
+        if (a % nR || b % nR) throw Err(ERR_GENERIC, "row ownership must be cut at left-row boundaries of the sector pairs");
+        lr0[p] = (int)(a / nR); lr1[p] = (int)(b / nR);
+    }
+    if (pair_cost) pair_cost->assign(np, 0.0);
     std::set<const void*> touched;
     long long tile_bytes = 0;
     auto touch = [&](const Tile& t) {
@@ -95,11 +127,12 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
             bool needV = false;
             if (G.A)
                 for (const Tile& t : G.A->tiles[il]) if (t.fmt != T_EYE) needV = true;
-            if (needV) { gp[g][p].voff = wtotal; wtotal += (long long)SL.size[il] * SR.size[jr]; }
+            if (lr1[p] <= lr0[p]) { gp[g][p].q = -1; continue; }
+            if (needV) { gp[g][p].voff = wtotal; wtotal += (long long)(lr1[p] - lr0[p]) * SR.size[jr]; }
         }
     }
-    H->work = std::make_shared<DevBuf>(ctx, std::max<long long>(1, wtotal) * 8);
-    double* W = H->work->as<double>();
+    if (!dry) H->work = std::make_shared<DevBuf>(ctx, std::max<long long>(1, wtotal) * 8);
+    double* W = dry ? nullptr : H->work->as<double>();
 
     /* ---- pre-summed right factors per (group, right row sector) ---- */
     struct BTile { Tile t; double coef; };
@@ -128,14 +161,17 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
                 if (same.size() == 1) { bt[g][ir].push_back(raw[a]); touch(raw[a].t); continue; }
                 /* Σ_j a_j B_j materialised once (device axpy over the contiguous panels) */
                 const long long cnt = (long long)raw[a].t.nr * raw[a].t.nc;
-                BufRef sum = std::make_shared<DevBuf>(ctx, cnt * 8);
-                for (size_t k = 0; k < same.size(); ++k) {
-                    const BTile& s = raw[same[k]];
-                    dev::axpby_out(ctx->st, k == 0 ? nullptr : sum->as<double>(), s.t.d, s.coef, sum->as<double>(), cnt);
-                }
-                H->keep.push_back(sum);
                 BTile merged = raw[a];
-                merged.t.d = sum->as<double>(); merged.t.owner = sum; merged.coef = 1.0;
+                if (!dry) {
+                    BufRef sum = std::make_shared<DevBuf>(ctx, cnt * 8);
+                    for (size_t k = 0; k < same.size(); ++k) {
+                        const BTile& s = raw[same[k]];
+                        dev::axpby_out(ctx->st, k == 0 ? nullptr : sum->as<double>(), s.t.d, s.coef, sum->as<double>(), cnt);
+                    }
+                    H->keep.push_back(sum);
+                    merged.t.d = sum->as<double>(); merged.t.owner = sum;
+                }
+                merged.coef = 1.0;
                 bt[g][ir].push_back(merged);
                 touch(merged.t);
             }
@@ -152,14 +188,17 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
             if (q < 0) continue;
             const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
             const int jl = il + G.sA, jr = ir + G.sB;
-            const int nLp = SL.size[il], nRq = SR.size[jr];
-            if (nLp == 0 || SR.size[ir] == 0 || nRq == 0 || SL.size[jl] == 0) continue;
+            const int nLp = lr1[p] - lr0[p], nRq = SR.size[jr];
+            if (nLp <= 0 || SR.size[ir] == 0 || nRq == 0 || SL.size[jl] == 0) continue;
             const long long xq = kron->off[q];
             std::vector<Tile> atiles;
-            if (G.A) atiles = G.A->tiles[il]; else atiles.push_back(full_eye(SL.off[il], nLp));
+            if (G.A) atiles = G.A->tiles[il]; else atiles.push_back(full_eye(SL.off[il], SL.size[il]));
             std::vector<Contribution> vcontrib;
-            for (const Tile& a : atiles) {
-                const int ra0 = a.r0 - SL.off[il], ca0 = a.c0 - SL.off[jl];
+            const double flops_before = H->stage1.flops;
+            for (Tile a : atiles) {
+                if (!clip_tile_rows(a, SL.off[il] + lr0[p], SL.off[il] + lr1[p])) continue;
+                /* rows are counted from the first owned row of the pair */
+                const int ra0 = a.r0 - SL.off[il] - lr0[p], ca0 = a.c0 - SL.off[jl];
                 /* --- the left factor --- */
                 const double* vsrc; int vflags; double acoef = 1.0;
                 if (a.fmt == T_EYE) {
@@ -206,28 +245,83 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
                 }
             }
             if (!vcontrib.empty()) emit_cells(H->stage1, W + gp[g][p].voff, false, nRq, nLp, nRq, vcontrib, false);
+            if (pair_cost) (*pair_cost)[p] += H->stage1.flops - flops_before;
         }
     }
     {   /* dry run to learn the total stage-2 work, then cut long chains so that the launch has ~5 waves of
            equal items on 148 SMs x 3 resident CTAs (v0 lost a third of the machine to a 1.4-wave tail) */
-        Plan dry;
+        Plan probe;
         for (int p = 0; p < np; ++p)
-            emit_cells(dry, yoff(kron->off[p]), true, SR.size[kron->pairs[p].ir], SL.size[kron->pairs[p].il], SR.size[kron->pairs[p].ir],
-                       ycontrib[p], true);
+            emit_cells(probe, yoff(kron->off[p]), true, SR.size[kron->pairs[p].ir], lr1[p] - lr0[p], SR.size[kron->pairs[p].ir], ycontrib[p], true);
         const double target_items = 148.0 * 3.0 * 5.0;
-        if (dry.flops > 0 && (double)dry.items.size() < target_items) H->stage2.split_item_cost = 0.5 * dry.flops / target_items;
+        if (probe.flops > 0 && (double)probe.items.size() < target_items) H->stage2.split_item_cost = 0.5 * probe.flops / target_items;
     }
     for (int p = 0; p < np; ++p) {
-        const int nLp = SL.size[kron->pairs[p].il], nRp = SR.size[kron->pairs[p].ir];
-        emit_cells(H->stage2, yoff(kron->off[p]), true, nRp, nLp, nRp, ycontrib[p], true);
+        const int nLp = lr1[p] - lr0[p], nRp = SR.size[kron->pairs[p].ir];
+        const double flops_before = H->stage2.flops;
+        /* y offsets are global: a rank that stores only its own rows passes y - row_begin as the base */
+        emit_cells(H->stage2, yoff(kron->off[p] + (long long)lr0[p] * nRp), true, nRp, nLp, nRp, ycontrib[p], true);
+        if (pair_cost) (*pair_cost)[p] += H->stage2.flops - flops_before;
     }
     tr.mark("plan");
-    H->stage1.upload(ctx);
-    H->stage2.upload(ctx);
+    if (!dry) {
+        H->stage1.upload(ctx);
+        H->stage2.upload(ctx);
+    }
     tr.mark("upload");
     H->alg_bytes = 16LL * H->n + tile_bytes;
     H->alg_flops = H->stage1.flops + H->stage2.flops;
     return H.release();
+}
+
+/* Row ownership of the ranks (a5, src/DMRGKron.cpp:1519-1704: contiguous row ranges with even predicted work; falls back
+   to an even split of rows when there is nothing to predict).  The prediction is the plan's own useful flops per sector
+   pair, spread evenly over the pair's left rows; cuts fall on left-row boundaries, on multiples of 16 rows where the pair
+   is large enough (whole DMMA fragments).  Every rank computes the same table. */
+static std::vector<long long> shard_rows(const Kron* kron, const std::vector<Group>& groups, int nterms, int world) {
+    const int np = (int)kron->pairs.size();
+    const long long n = kron->nstates();
+    std::vector<long long> cuts(world + 1, n);
+    cuts[0] = 0;
+    if (world <= 1) return cuts;
+    std::vector<double> cost;
+    { std::unique_ptr<HShell> probe(build_shell(kron, groups, nterms, 0, -1, true, &cost)); }
+    const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
+    double total = 0;
+    for (int p = 0; p < np; ++p) {
+        if (cost[p] <= 0) cost[p] = (double)kron->pairs[p].size; /* sparse / identity-only pairs: count rows */
+        total += cost[p];
+    }
+    if (total <= 0) { for (int r = 1; r < world; ++r) cuts[r] = 0; return cuts; }
+    double cum = 0;
+    int r = 1;
+    for (int p = 0; p < np && r < world; ++p) {
+        const long long nL = SL.size[kron->pairs[p].il], nR = SR.size[kron->pairs[p].ir];
+        while (r < world && cost[p] > 0 && total * r / world <= cum + cost[p]) {
+            const double frac = (total * r / world - cum) / cost[p];
+            long long l = (long long)std::llround(frac * (double)nL);
+            if (nL >= 64) l = ((l + 8) / 16) * 16;
+            l = std::max<long long>(0, std::min(l, nL));
+            cuts[r] = std::max(cuts[r - 1], kron->off[p] + l * nR);
+            ++r;
+        }
+        cum += cost[p];
+    }
+    for (; r < world; ++r) cuts[r] = n;
+    return cuts;
+}
+
+static HShell* build_sharded(const Kron* kron, const std::vector<Group>& groups, int nterms) {
+    Ctx* ctx = kron->ctx;
+    if (ctx->world <= 1) {
+        HShell* H = build_shell(kron, groups, nterms);
+        H->row_cuts = {0, H->n};
+        return H;
+    }
+    const std::vector<long long> cuts = shard_rows(kron, groups, nterms, ctx->world);
+    HShell* H = build_shell(kron, groups, nterms, cuts[ctx->rank], cuts[ctx->rank + 1]);
+    H->row_cuts = cuts;
+    return H;
 }
 
 /* src/DMRGKron.cpp:759-841 (classification, reflection) + :891-989 (term list = H_L⊗1, 1⊗H_R, LR terms) */
@@ -263,7 +357,7 @@ HShell* hshell_create(const Kron* kron, const std::vector<Term>& terms) {
         if (f == gidx.end()) { gidx[key] = groups.size(); groups.push_back({A, t.Iop, t.Jop, {}}); f = gidx.find(key); }
         groups[f->second].rights.push_back({t.a, B});
     }
-    return build_shell(kron, groups, 2 + (int)lr.size());
+    return build_sharded(kron, groups, 2 + (int)lr.size());
 }
 
 /* KronConstruct, include/DMRGKron.hpp:309 / src/DMRGKron.cpp:618-694: one term 1.0 · A ⊗ B (correlators) */
@@ -272,7 +366,7 @@ HShell* hshell_create_single(const Kron* kron, int opl, int il, int opr, int ir)
     const Operator* B = opr == OP_EYE ? nullptr : kron->R->op(opr, ir);
     std::vector<Group> groups;
     groups.push_back({A, opl == OP_EYE ? 0 : opl, opr == OP_EYE ? 0 : opr, {{1.0, B}}});
-    return build_shell(kron, groups, 1);
+    return build_sharded(kron, groups, 1);
 }
 
 /* Product O_1·O_2·…·O_k of operators of ONE block (CalculateOperatorProducts, include/DMRGBlockContainer.hpp:2340-2425:
@@ -361,7 +455,7 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
     const Operator* B = factor(kron->R, rops, sB);
     std::vector<Group> groups;
     groups.push_back({A, sA, sB, {{1.0, B}}});
-    HShell* H = build_shell(kron, groups, 1);
+    HShell* H = build_sharded(kron, groups, 1);
     H->keep.insert(H->keep.end(), keep.begin(), keep.end());
     H->keep_ops = keep_ops;
     return H;
@@ -371,6 +465,14 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
     H->stage1.run(H->ctx, d_x, nullptr);
     H->stage2.run(H->ctx, d_x, d_y);
+}
+
+/* The distributed form of the callback: x is a full-length buffer in which only this rank's rows are valid on entry;
+   the exchange step of the path (the VecScatter-to-all of src/DMRGKron.cpp:1833-1834) is an in-place all-gather over
+   NVLink, after which this rank computes its own rows of y. */
+void hshell_apply_sharded(HShell* H, double* d_x, double* d_y) {
+    if (H->ctx->world > 1) dev::allgatherv(H->ctx->st, d_x, H->row_cuts.data());
+    hshell_apply(H, d_x, d_y);
 }
 
 }  // namespace dmrgx

@@ -29,12 +29,12 @@ struct Eigen_t { double eigval; int seqIdx, epsIdx, blkIdx; };
 struct SideJob {
     bool left;
     std::vector<long long> roff, woff;
-    std::vector<int> dim, blkidx;
+    std::vector<int> dim, blkidx, owner; /* owner: rank that builds and diagonalises the block */
     long long wtot = 0;
     BufRef rho, dw;
 };
 
-static void side_build_rho(const Kron* kron, const double* d_psi, bool left, SideJob& J) {
+static void side_layout(const Kron* kron, bool left, SideJob& J) {
     Ctx* ctx = kron->ctx;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     const int np = (int)kron->pairs.size();
@@ -51,11 +51,19 @@ static void side_build_rho(const Kron* kron, const double* d_psi, bool left, Sid
     J.wtot = J.woff[np];
     J.rho = std::make_shared<DevBuf>(ctx, std::max<long long>(1, J.roff.back()) * 8);
     J.dw = std::make_shared<DevBuf>(ctx, std::max<long long>(1, J.wtot) * 8);
+    J.owner.assign(np, 0);
+}
+
+static void side_build_rho(const Kron* kron, const double* d_psi, SideJob& J) {
+    Ctx* ctx = kron->ctx;
+    const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
+    const int np = (int)kron->pairs.size();
+    const bool left = J.left;
     Plan plan;
     for (int p = 0; p < np; ++p) {
         const int nL = SL.size[kron->pairs[p].il], nR = SR.size[kron->pairs[p].ir];
         const int n = J.dim[p];
-        if (n == 0) continue;
+        if (n == 0 || J.owner[p] != ctx->rank) continue;
         Contribution c;
         c.r0 = 0; c.c0 = 0; c.nr = n; c.nc = n;
         c.seg = make_seg(dev::SEG_GEMM);
@@ -137,22 +145,54 @@ static XForm* side_select(const Kron* kron, long long mstates, const SideJob& J)
 
 void truncate(const Kron* kron, const double* d_psi, long long mstates, XForm** L, XForm** R) {
     Trace tr(kron->ctx, "truncate");
+    Ctx* ctx = kron->ctx;
     SideJob JL, JR;
-    side_build_rho(kron, d_psi, true, JL);
-    side_build_rho(kron, d_psi, false, JR);
+    side_layout(kron, true, JL);
+    side_layout(kron, false, JR);
+    /* The reference gathers psi to rank 0 and diagonalises every block there, serially (:1675-1775).  Here psi is
+       already complete on every rank; the blocks of both sides are dealt to the ranks largest-first (n^3 cost, greedy
+       least-loaded, the same table on every rank), each rank builds and diagonalises its own, and the eigenvectors and
+       eigenvalues are then broadcast from their owners in one NCCL group. */
+    if (ctx->world > 1) {
+        struct Ref { SideJob* J; int p; double cost; };
+        std::vector<Ref> refs;
+        for (SideJob* J : {&JL, &JR})
+            for (size_t p = 0; p < J->dim.size(); ++p)
+                if (J->dim[p] > 0) refs.push_back({J, (int)p, std::pow((double)J->dim[p], 3.0)});
+        std::stable_sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) { return a.cost > b.cost; });
+        std::vector<double> load(ctx->world, 0.0);
+        for (const Ref& r : refs) {
+            int best = 0;
+            for (int k = 1; k < ctx->world; ++k) if (load[k] < load[best]) best = k;
+            r.J->owner[r.p] = best;
+            load[best] += r.cost + 1e6; /* per-call latency of a small eigensolve */
+        }
+    }
+    side_build_rho(kron, d_psi, JL);
+    side_build_rho(kron, d_psi, JR);
     tr.mark("rho");
     /* ---- full spectrum of every block of both sides (EPSLAPACK, all n pairs, :1976-1994) ---- */
     std::vector<int> n;
     std::vector<double*> A, W;
     for (SideJob* J : {&JL, &JR})
         for (size_t p = 0; p < J->dim.size(); ++p) {
-            if (J->dim[p] == 0) continue;
+            if (J->dim[p] == 0 || J->owner[p] != ctx->rank) continue;
             n.push_back(J->dim[p]);
             A.push_back(J->rho->as<double>() + J->roff[p]);
             W.push_back(J->dw->as<double>() + J->woff[p]);
         }
-    const int e = dev::syevd_batch(kron->ctx->st, (int)n.size(), n.data(), A.data(), W.data());
+    const int e = dev::syevd_batch(ctx->st, (int)n.size(), n.data(), A.data(), W.data());
     if (e) throw Err(ERR_GENERIC, std::string("eigendecomposition of a reduced density matrix block failed: ") + dev::last_error());
+    if (ctx->world > 1) {
+        std::vector<double*> ptr; std::vector<long long> cnt; std::vector<int> root;
+        for (SideJob* J : {&JL, &JR})
+            for (size_t p = 0; p < J->dim.size(); ++p) {
+                if (J->dim[p] == 0) continue;
+                ptr.push_back(J->rho->as<double>() + J->roff[p]); cnt.push_back((long long)J->dim[p] * J->dim[p]); root.push_back(J->owner[p]);
+                ptr.push_back(J->dw->as<double>() + J->woff[p]); cnt.push_back(J->dim[p]); root.push_back(J->owner[p]);
+            }
+        dev::bcast_batch(ctx->st, (int)ptr.size(), ptr.data(), cnt.data(), root.data());
+    }
     tr.mark("syevd_batch");
     std::unique_ptr<XForm> l(side_select(kron, mstates, JL));
     std::unique_ptr<XForm> r(side_select(kron, mstates, JR));
@@ -184,18 +224,24 @@ Block* rotate(const Block* enl, const XForm* xf) {
     long long ttot = 0, otot = 0;
     struct Blk { int job, I, J, Ip, Jp; long long toff, ooff; };
     std::vector<Blk> blks;
+    /* Multi-GPU: operator j is rotated by rank j mod world and its panels (contiguous in the output buffer) are then
+       broadcast from there; the reference's counterpart is the -rot_nsubcomm split of src/DMRGBlock.cpp:700-760. */
+    const int world = ctx->world, rank = ctx->rank;
+    std::vector<long long> job_o0(jobs.size() + 1, 0);
     for (size_t j = 0; j < jobs.size(); ++j) {
         const Operator& O = *jobs[j].src;
+        job_o0[j] = otot;
         for (int Ip = 0; Ip < nn; ++Ip) {
             const int I = xf->old_sector[Ip], J = I + O.shift;
             if (J < 0 || J >= SO.nsec()) continue;
             const int Jp = new_of_old[J];
             if (Jp < 0 || O.tiles[I].empty()) continue;
             blks.push_back({(int)j, I, J, Ip, Jp, ttot, otot});
-            ttot += (long long)SO.size[I] * SN.size[Jp];
+            if ((int)(j % world) == rank) ttot += (long long)SO.size[I] * SN.size[Jp];
             otot += (long long)SN.size[Ip] * SN.size[Jp];
         }
     }
+    job_o0[jobs.size()] = otot;
     tr.mark("setup");
     BufRef tbuf = std::make_shared<DevBuf>(ctx, std::max<long long>(1, ttot) * 8);
     BufRef obuf = std::make_shared<DevBuf>(ctx, std::max<long long>(1, otot) * 8);
@@ -208,6 +254,10 @@ Block* rotate(const Block* enl, const XForm* xf) {
         const double* UI = xf->U[b.Ip]->as<double>(); /* mI × nI */
         double* T = tbuf->as<double>() + b.toff;      /* nI × mJ */
         double* Oo = obuf->as<double>() + b.ooff;     /* mI × mJ */
+        Tile o;
+        o.fmt = T_DENSE; o.r0 = SN.off[b.Ip]; o.c0 = SN.off[b.Jp]; o.nr = mI; o.nc = mJ; o.d = Oo; o.sr = mJ; o.sc = 1; o.owner = obuf;
+        jobs[b.job].dst->tiles[b.Ip].push_back(o);
+        if (b.job % world != rank) continue;
         std::vector<Contribution> cs;
         for (const Tile& t : O.tiles[b.I]) {
             const int ra0 = t.r0 - SO.off[b.I], ca0 = t.c0 - SO.off[b.J];
@@ -235,9 +285,6 @@ Block* rotate(const Block* enl, const XForm* xf) {
         c.seg.B = T; c.seg.ldb_k = mJ; c.seg.ldb_n = 1;
         std::vector<Contribution> c2 = {c};
         emit_cells(p2, Oo, false, mJ, mI, mJ, c2, true);
-        Tile o;
-        o.fmt = T_DENSE; o.r0 = SN.off[b.Ip]; o.c0 = SN.off[b.Jp]; o.nr = mI; o.nc = mJ; o.d = Oo; o.sr = mJ; o.sc = 1; o.owner = obuf;
-        jobs[b.job].dst->tiles[b.Ip].push_back(o);
     }
     for (Job& j : jobs) { j.dst->shift = j.src->shift; j.dst->present = true; }
     tr.mark("plan");
@@ -248,6 +295,15 @@ Block* rotate(const Block* enl, const XForm* xf) {
     tr.mark("run1");
     p2.run(ctx);
     tr.mark("run2");
+    if (world > 1) {
+        std::vector<double*> ptr; std::vector<long long> cnt; std::vector<int> root;
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            if (job_o0[j + 1] == job_o0[j]) continue;
+            ptr.push_back(obuf->as<double>() + job_o0[j]); cnt.push_back(job_o0[j + 1] - job_o0[j]); root.push_back((int)(j % world));
+        }
+        dev::bcast_batch(ctx->st, (int)ptr.size(), ptr.data(), cnt.data(), root.data());
+        tr.mark("bcast");
+    }
     /* Sm' = (Sp')ᵀ as views (the reference rebuilds Sm on demand, src/DMRGBlock.cpp:623-636) */
     for (int i = 0; i < out->nsites; ++i) {
         Operator& sm = out->Sm[i];

@@ -40,6 +40,14 @@ dmrgx_int dmrgx_launch_count(void);
 /* ---- context: one CUDA device + stream (replaces the MPI communicator of the reference objects) ---- */
 /* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create a private one */
 int dmrgx_ctx_create(int device, void* stream, dmrgx_ctx* out);
+/* Multi-GPU: one process per GPU.  Rank 0 obtains a 128-byte communicator id (an ncclUniqueId) and the launcher hands it
+   to the other ranks (torch.distributed broadcast in bench.py, a file in the driver); every rank then creates its context
+   with its rank.  This replaces the MPI communicator the reference objects are created on (MPI_Comm_rank/size,
+   include/DMRGBlockContainer.hpp:279-280).  Objects created on such a context are sharded by superblock row ranges:
+   the successor of KronSumShellSplitOwnership (src/DMRGKron.cpp:1519-1704). */
+int dmrgx_dist_unique_id(void* out128);
+int dmrgx_ctx_create_dist(int device, void* stream, int rank, int world, const void* id128, dmrgx_ctx* out);
+int dmrgx_ctx_rank(dmrgx_ctx ctx, int* rank, int* world);
 int dmrgx_ctx_destroy(dmrgx_ctx ctx);
 int dmrgx_ctx_sync(dmrgx_ctx ctx);
 /* fill fraction above which a sector-block panel is stored dense (default 0.125) */
@@ -97,10 +105,17 @@ int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, cons
                                 const dmrgx_int* rsite, dmrgx_hshell* out);
 /* MatMult_KronSumShell(A, x, y): src/DMRGKron.cpp:1827-1869.  Device pointers, length NumStates(). */
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y);
+/* The distributed form of the same callback.  d_x: full-length device buffer in which this rank's rows are valid on entry;
+   the VecScatter-to-all of src/DMRGKron.cpp:1833-1834 becomes an in-place NCCL all-gather, then this rank's rows of d_y
+   (also a full-length buffer) are computed.  On one GPU identical to dmrgx_hshell_apply. */
+int dmrgx_hshell_apply_sharded(dmrgx_hshell h, double* d_x, double* d_y);
+/* rows [begin,end) this rank owns; cuts (optional, world+1 entries) = the ownership table of all ranks */
+int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmrgx_int* cuts);
 /* profiling aids: run only stage 1 (V = A·X panels) or stage 2 (Y = Σ V·Bᵀ) of an apply, and their useful flops */
 int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y);
 int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
-/* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, apply, D2H, synchronous */
+/* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, (all-gather,) apply, D2H, synchronous.  x and y are
+   this rank's LOCAL rows, as VecGetArray returns them on the reference's MPI vectors — the whole vector on one GPU. */
 int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y);
 /* MatDestroy_KronSumShell: src/DMRGKron.cpp:1919-1942 */
 int dmrgx_hshell_destroy(dmrgx_hshell h);

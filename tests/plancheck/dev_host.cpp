@@ -106,9 +106,9 @@ static unsigned long long splitmix64(unsigned long long z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
-void fill_random(Stream*, double* x, long long n, unsigned long long seed) {
+void fill_random(Stream*, double* x, long long n, unsigned long long seed, long long first) {
     ++g_launches;
-    for (long long i = 0; i < n; ++i) x[i] = (double)(splitmix64(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL) >> 11) / 9007199254740992.0 - 0.5;
+    for (long long i = 0; i < n; ++i) x[i] = (double)(splitmix64(seed + (unsigned long long)(first + i) * 0x9E3779B97F4A7C15ULL) >> 11) / 9007199254740992.0 - 0.5;
 }
 void multidot(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, double* out) {
     ++g_launches;
@@ -180,4 +180,29 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* A, double*
     return 0;
 }
 
+/* collectives of the emulation: callbacks registered by the test (tests/test_dist_cpu.py implements them with
+   torch.distributed over gloo, one process per emulated GPU) */
+typedef void (*allreduce_cb_t)(double* buf, long long n);
+typedef void (*bcast_cb_t)(double* buf, long long n, int root);
+static allreduce_cb_t g_allreduce = nullptr;
+static bcast_cb_t g_bcast = nullptr;
+static int g_rank = 0, g_world = 1;
+int comm_unique_id(void* out) { std::memset(out, 0, COMM_ID_BYTES); return 0; }
+int comm_init(Stream*, int rank, int world, const void*) { g_rank = rank; g_world = world; return 0; }
+int comm_rank(Stream*) { return g_rank; }
+int comm_world(Stream*) { return g_world; }
+void allreduce_sum(Stream*, double* buf, long long n) { if (g_world > 1 && n > 0) g_allreduce(buf, n); }
+void allgatherv(Stream*, double* buf, const long long* off) {
+    if (g_world <= 1) return;
+    for (int r = 0; r < g_world; ++r) if (off[r + 1] > off[r]) g_bcast(buf + off[r], off[r + 1] - off[r], r);
+}
+void bcast_batch(Stream*, int n, double* const* ptr, const long long* count, const int* root) {
+    if (g_world <= 1) return;
+    for (int i = 0; i < n; ++i) if (count[i] > 0) g_bcast(ptr[i], count[i], root[i]);
+}
+
 }  // namespace dev
+extern "C" void plancheck_set_collectives(void (*allreduce)(double*, long long), void (*bcast)(double*, long long, int)) {
+    dev::g_allreduce = allreduce;
+    dev::g_bcast = bcast;
+}
