@@ -202,22 +202,32 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    uid = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        P.use_library(None)
+        # rank 0 creates the communicator id of the library's own NCCL communicator; torch.distributed is only the courier
+        box = [P.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
     P.use_library(None)
     # a dedicated torch stream: the library launches on it and torch.cuda.Event records on it (the legacy default
     # stream has handle 0, which the C ABI reads as "create a private stream" — events would then miss the kernels)
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     assert tstream.cuda_stream != 0
-    ctx = P.Context(local, tstream.cuda_stream)
+    ctx = P.Context(local, tstream.cuda_stream, rank, world, uid)
     wl = W.Workload(P, ctx, args.config, m=args.m)
     H = wl.shell
     st = H.stats()
     n = wl.n
-    x = ctx.vec(n, wl.random_state())
+    rb, re_, cuts = H.row_range()
+    # the superblock vector is sharded by row ranges: every rank holds its own rows, an apply all-gathers x over NVLink
+    xin = np.zeros(n); xin[rb:re_] = wl.random_state()[rb:re_]
+    x = ctx.vec(n, xin)
     y = ctx.vec(n)
+    apply_fn = (lambda: H.MatMult_sharded(x, y)) if world > 1 else (lambda: H.MatMult(x, y))
 
     def barrier():
         if world > 1:
@@ -225,7 +235,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
-        H.MatMult(x, y)
+        apply_fn()
     peak_fp64 = fp64_peak_tflops(torch, dev)
     sampler = ClockSampler(local)
     barrier()
@@ -234,7 +244,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        H.MatMult(x, y)
+        apply_fn()
     e1.record()
     barrier()
     launches = P.launch_count() - l0
@@ -245,7 +255,7 @@ def main():
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
     ms = float(t_local.item())
     ms_step = ms / args.steps
-    value = world * st["alg_bytes"] / (ms_step * 1e-3) / 1e9  # replicas: every rank applies the whole H
+    value = st["alg_bytes_global"] / (ms_step * 1e-3) / 1e9  # one H*psi of the whole superblock, sharded over the ranks
 
     # per-stage timing of the dominant kernel (chain_kernel) for the roofline
     f1, f2 = H.stage_flops()
@@ -274,8 +284,8 @@ def main():
         lz = {"error": repr(exc)}
 
     # e2e: the reference-facing call with HOST buffers, copies inside the timed region
-    hx = torch.from_numpy(wl.random_state(2)).pin_memory()
-    hy = torch.empty(n, dtype=torch.float64).pin_memory()
+    hx = torch.from_numpy(wl.random_state(2)[rb:re_].copy()).pin_memory()   # this rank's local rows, like VecGetArray
+    hy = torch.empty(re_ - rb, dtype=torch.float64).pin_memory()
     hxn, hyn = hx.numpy(), hy.numpy()
     for _ in range(3):
         H.MatMult_host(hxn, hyn)
@@ -289,16 +299,17 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e.item()) / args.steps
-    e2e_val = world * st["alg_bytes"] / (ms_e2e * 1e-3) / 1e9
+    e2e_val = st["alg_bytes_global"] / (ms_e2e * 1e-3) / 1e9
 
     line = {
         "metric": "superblock H*psi algorithmic GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s m=%d sweep-midpoint superblock H*psi, D=%d, T=%d shell terms" % (args.config, args.m, n, st["nterms"]),
-                   "l2": "operator panels (%.0f MB) exceed the 126 MB L2, no flush needed" % ((st["alg_bytes"] - 16 * n) / 1e6),
-                   "parallelism": "replicas" if world > 1 else "single"},
-        "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n, "ms_per_step": ms_e2e},
+                   "l2": "operator panels (%.0f MB) exceed the 126 MB L2, no flush needed" % ((st["alg_bytes_global"] - 16 * n) / 1e6),
+                   "parallelism": ("superblock rows sharded over %d GPUs (cuts %s), NCCL all-gather of psi per apply" % (world, cuts.tolist()))
+                   if world > 1 else "single"},
+        "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * (re_ - rb), "d2h_bytes_per_step": 8 * (re_ - rb), "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s", "frac": achieved / peak_fp64,
@@ -307,7 +318,7 @@ def main():
                      "stage_ms": [t1, t2], "stage_flops": [f1, f2],
                      "hbm_frac_of_%s_peak" % peaks_kind: (st["alg_bytes"] / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"]},
         "lanczos": lz,
-        "alg": {"bytes_per_apply": st["alg_bytes"], "flops_per_apply": st["alg_flops"], "D": n,
+        "alg": {"bytes_per_apply": st["alg_bytes_global"], "flops_per_apply": st["alg_flops_global"], "rank0_flops": st["alg_flops"], "D": n,
                 "tiles": [st["tiles_stage1"], st["tiles_stage2"]]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -181,6 +181,10 @@ int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
     });
 }
 int dmrgx_hshell_destroy(dmrgx_hshell h) { return guard([&] { if (h) { dev::sync(H(h)->ctx->st); delete H(h); } }); }
+int dmrgx_hshell_stats_global(dmrgx_hshell h, double* alg_bytes, double* alg_flops) {
+    *alg_bytes = (double)H(h)->alg_bytes_global; *alg_flops = H(h)->alg_flops_global;
+    return 0;
+}
 int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, double* alg_bytes, double* alg_flops, dmrgx_int* nt1, dmrgx_int* nt2) {
     HShell* s = H(h);
     if (nstates) *nstates = s->n;

@@ -145,6 +145,8 @@ struct HShell {
     std::vector<std::shared_ptr<Operator>> keep_ops; /* operator products of correlators */
     long long alg_bytes = 0;     /* 16*D + distinct operator tile bytes */
     double alg_flops = 0;
+    long long alg_bytes_global = 0; /* the same two figures for the whole (unsharded) operator */
+    double alg_flops_global = 0;
     int nterms = 0;
     ~HShell();
 };

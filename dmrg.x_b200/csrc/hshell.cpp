@@ -173,7 +173,7 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
                 }
                 merged.coef = 1.0;
                 bt[g][ir].push_back(merged);
-                touch(merged.t);
+                for (size_t k = 0; k < same.size(); ++k) touch(raw[same[k]].t); /* algorithmic bytes count the ORIGINAL panels once each */
             }
         }
     }
@@ -278,14 +278,15 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
    to an even split of rows when there is nothing to predict).  The prediction is the plan's own useful flops per sector
    pair, spread evenly over the pair's left rows; cuts fall on left-row boundaries, on multiples of 16 rows where the pair
    is large enough (whole DMMA fragments).  Every rank computes the same table. */
-static std::vector<long long> shard_rows(const Kron* kron, const std::vector<Group>& groups, int nterms, int world) {
+static std::vector<long long> shard_rows(const Kron* kron, const std::vector<Group>& groups, int nterms, int world, long long& global_bytes,
+                                         double& global_flops) {
     const int np = (int)kron->pairs.size();
     const long long n = kron->nstates();
     std::vector<long long> cuts(world + 1, n);
     cuts[0] = 0;
     if (world <= 1) return cuts;
     std::vector<double> cost;
-    { std::unique_ptr<HShell> probe(build_shell(kron, groups, nterms, 0, -1, true, &cost)); }
+    { std::unique_ptr<HShell> probe(build_shell(kron, groups, nterms, 0, -1, true, &cost)); global_bytes = probe->alg_bytes; global_flops = probe->alg_flops; }
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     double total = 0;
     for (int p = 0; p < np; ++p) {
@@ -316,11 +317,14 @@ static HShell* build_sharded(const Kron* kron, const std::vector<Group>& groups,
     if (ctx->world <= 1) {
         HShell* H = build_shell(kron, groups, nterms);
         H->row_cuts = {0, H->n};
+        H->alg_bytes_global = H->alg_bytes; H->alg_flops_global = H->alg_flops;
         return H;
     }
-    const std::vector<long long> cuts = shard_rows(kron, groups, nterms, ctx->world);
+    long long gb = 0; double gf = 0;
+    const std::vector<long long> cuts = shard_rows(kron, groups, nterms, ctx->world, gb, gf);
     HShell* H = build_shell(kron, groups, nterms, cuts[ctx->rank], cuts[ctx->rank + 1]);
     H->row_cuts = cuts;
+    H->alg_bytes_global = gb; H->alg_flops_global = gf;
     return H;
 }
 

@@ -224,9 +224,12 @@ Block* rotate(const Block* enl, const XForm* xf) {
     long long ttot = 0, otot = 0;
     struct Blk { int job, I, J, Ip, Jp; long long toff, ooff; };
     std::vector<Blk> blks;
-    /* Multi-GPU: operator j is rotated by rank j mod world and its panels (contiguous in the output buffer) are then
-       broadcast from there; the reference's counterpart is the -rot_nsubcomm split of src/DMRGBlock.cpp:700-760. */
+    /* Multi-GPU: the operators are dealt to the ranks in contiguous runs (every Sz_i / Sp_i costs the same), so each rank's
+       output is ONE contiguous range of the output buffer and the exchange is a single in-place all-gather; the reference's
+       counterpart is the -rot_nsubcomm split of src/DMRGBlock.cpp:700-760. */
     const int world = ctx->world, rank = ctx->rank;
+    const size_t njobs = jobs.size();
+    auto owner_of = [&](size_t j) { return (int)((j * (size_t)world) / njobs); };
     std::vector<long long> job_o0(jobs.size() + 1, 0);
     for (size_t j = 0; j < jobs.size(); ++j) {
         const Operator& O = *jobs[j].src;
@@ -237,7 +240,7 @@ Block* rotate(const Block* enl, const XForm* xf) {
             const int Jp = new_of_old[J];
             if (Jp < 0 || O.tiles[I].empty()) continue;
             blks.push_back({(int)j, I, J, Ip, Jp, ttot, otot});
-            if ((int)(j % world) == rank) ttot += (long long)SO.size[I] * SN.size[Jp];
+            if (owner_of(j) == rank) ttot += (long long)SO.size[I] * SN.size[Jp];
             otot += (long long)SN.size[Ip] * SN.size[Jp];
         }
     }
@@ -257,7 +260,7 @@ Block* rotate(const Block* enl, const XForm* xf) {
         Tile o;
         o.fmt = T_DENSE; o.r0 = SN.off[b.Ip]; o.c0 = SN.off[b.Jp]; o.nr = mI; o.nc = mJ; o.d = Oo; o.sr = mJ; o.sc = 1; o.owner = obuf;
         jobs[b.job].dst->tiles[b.Ip].push_back(o);
-        if (b.job % world != rank) continue;
+        if (owner_of((size_t)b.job) != rank) continue;
         std::vector<Contribution> cs;
         for (const Tile& t : O.tiles[b.I]) {
             const int ra0 = t.r0 - SO.off[b.I], ca0 = t.c0 - SO.off[b.J];
@@ -296,12 +299,14 @@ Block* rotate(const Block* enl, const XForm* xf) {
     p2.run(ctx);
     tr.mark("run2");
     if (world > 1) {
-        std::vector<double*> ptr; std::vector<long long> cnt; std::vector<int> root;
-        for (size_t j = 0; j < jobs.size(); ++j) {
-            if (job_o0[j + 1] == job_o0[j]) continue;
-            ptr.push_back(obuf->as<double>() + job_o0[j]); cnt.push_back(job_o0[j + 1] - job_o0[j]); root.push_back((int)(j % world));
+        std::vector<long long> cuts(world + 1, otot);
+        cuts[0] = 0;
+        for (int r = 1; r < world; ++r) { /* first output element of the first operator owned by a rank >= r */
+            size_t j = 0;
+            while (j < njobs && owner_of(j) < r) ++j;
+            cuts[r] = job_o0[j];
         }
-        dev::bcast_batch(ctx->st, (int)ptr.size(), ptr.data(), cnt.data(), root.data());
+        dev::allgatherv(ctx->st, obuf->as<double>(), cuts.data());
         tr.mark("bcast");
     }
     /* Sm' = (Sp')ᵀ as views (the reference rebuilds Sm on demand, src/DMRGBlock.cpp:623-636) */

@@ -9,6 +9,8 @@
  */
 static char help[] = "DMRG executable for the Spin-1/2 J1-J2 XY Model on a two-dimensional square lattice (B200 path).\n";
 
+#include <unistd.h>
+
 #include "DMRGBlock.hpp"
 #include "DMRGBlockContainer.hpp"
 #include "Hamiltonians.hpp"
@@ -32,9 +34,36 @@ int main(int argc, char** argv) {
             o.Insert(argc, argv); /* the command line wins */
         }
     }
-    PetscInt device = 0;
+    /* One process per GPU.  Launched by `python -m torch.distributed.run --no-python --nproc-per-node N …` (or any launcher
+       that sets RANK / WORLD_SIZE / LOCAL_RANK): rank 0 creates the communicator id and passes it on through a file, every
+       rank drives the GPU of its LOCAL_RANK, and only rank 0 prints and writes the JSON files of -data_dir. */
+    auto env_int = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
+    const int rank = env_int("RANK", 0), world = env_int("WORLD_SIZE", 1);
+    PetscInt device = env_int("LOCAL_RANK", 0);
     o.GetInt("-device", &device, NULL);
-    if (dmrgx_ctx_create((int)device, NULL, &DmrgxContext())) {
+    if (world > 1) {
+        unsigned char id[128];
+        const char* idf = getenv("DMRGX_ID_FILE");
+        const std::string id_file = idf ? idf : std::string("/tmp/dmrgx_id_") + (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+        if (rank == 0) {
+            if (dmrgx_dist_unique_id(id)) { fprintf(stderr, "[dmrgx] %s\n", dmrgx_last_error()); return 110; }
+            FILE* f = fopen((id_file + ".tmp").c_str(), "wb");
+            if (!f || fwrite(id, 1, 128, f) != 128) { fprintf(stderr, "cannot write %s\n", id_file.c_str()); return 1; }
+            fclose(f);
+            rename((id_file + ".tmp").c_str(), id_file.c_str());
+        } else {
+            FILE* f = nullptr;
+            for (int tries = 0; tries < 6000 && !(f = fopen(id_file.c_str(), "rb")); ++tries) usleep(10000);
+            if (!f || fread(id, 1, 128, f) != 128) { fprintf(stderr, "rank %d: cannot read the communicator id from %s\n", rank, id_file.c_str()); return 1; }
+            fclose(f);
+            if (!freopen("/dev/null", "w", stdout)) return 1;
+            std::string dd = "./data_dir/"; PetscBool set;
+            o.GetString("-data_dir", dd, &set);
+            o.kv["-data_dir"] = dd + (dd.back() == '/' ? "" : "/") + ".rank" + std::to_string(rank) + "/";
+        }
+        if (dmrgx_ctx_create_dist((int)device, NULL, rank, world, id, &DmrgxContext())) { fprintf(stderr, "[dmrgx] %s\n", dmrgx_last_error()); return 100; }
+        if (rank == 0) remove(id_file.c_str()); /* the communicator exists: every rank has read it */
+    } else if (dmrgx_ctx_create((int)device, NULL, &DmrgxContext())) {
         fprintf(stderr, "[dmrgx] %s\n", dmrgx_last_error());
         return 100;
     }

@@ -123,6 +123,9 @@ int dmrgx_hshell_destroy(dmrgx_hshell h);
 int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, double* alg_bytes, double* alg_flops,
                        dmrgx_int* ntiles_stage1, dmrgx_int* ntiles_stage2);
 
+/* the algorithmic bytes / flops of the WHOLE operator on a multi-GPU context (dmrgx_hshell_stats then reports this rank's share) */
+int dmrgx_hshell_stats_global(dmrgx_hshell h, double* alg_bytes, double* alg_flops);
+
 /* ---- ground state: EPSSolve + EPSGetEigenpair(0), include/DMRGBlockContainer.hpp:1484-1500 ---- */
 typedef struct {
     double tol;               /* -H_eps_tol    (SLEPc default 1e-8)  */
