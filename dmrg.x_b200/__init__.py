@@ -343,6 +343,11 @@ class HShell:
         _chk(lib().dmrgx_hshell_stage_flops(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def stage_exec_flops(self):
+        a, b = C.c_double(), C.c_double()
+        _chk(lib().dmrgx_hshell_stage_exec_flops(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def MatMult_host(self, x, y=None):
         """The PETSc-callback shape: host arrays in and out (H2D + kernels + D2H inside).  On a multi-GPU context x and y
         are this rank's local rows (VecGetArray of an MPI Vec)."""

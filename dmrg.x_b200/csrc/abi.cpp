@@ -4,7 +4,10 @@
 #include <string>
 
 #include "../../include/dmrgx.h"
+#include <cmath>
+
 #include "common.h"
+#include "plan.h"
 
 using namespace dmrgx;
 
@@ -163,6 +166,25 @@ int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops1, double* flops2) {
     *flops1 = H(h)->stage1.flops; *flops2 = H(h)->stage2.flops;
     return 0;
 }
+/* plan introspection (profiling aid): per work item of a stage {tm, tn, number of segments, sum of K over GEMM segments};
+   returns the number of items (fills at most cap) */
+dmrgx_int dmrgx_hshell_plan_items(dmrgx_hshell h, int stage, dmrgx_int cap, dmrgx_int* out4) {
+    const Plan& p = stage == 1 ? H(h)->stage1 : H(h)->stage2;
+    dmrgx_int n = 0;
+    for (const dev::WorkItem& it : p.items) {
+        if (n < cap) {
+            long long ks = 0;
+            for (int sgi = it.seg_begin; sgi < it.seg_end; ++sgi) if (p.segs[sgi].type == dev::SEG_GEMM) ks += p.segs[sgi].K;
+            out4[4 * n] = it.tm; out4[4 * n + 1] = it.tn; out4[4 * n + 2] = it.seg_end - it.seg_begin; out4[4 * n + 3] = ks;
+        }
+        ++n;
+    }
+    return n;
+}
+int dmrgx_hshell_stage_exec_flops(dmrgx_hshell h, double* flops1, double* flops2) {
+    *flops1 = H(h)->stage1.exec_flops; *flops2 = H(h)->stage2.exec_flops;
+    return 0;
+}
 int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
     return guard([&] {
         HShell* s = H(h);
@@ -268,6 +290,51 @@ int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value) {
         dev::allreduce_sum(ctx->st, d_out, 1);
         dev::d2h(ctx->st, value, d_out, 8);
         dev::sync(ctx->st);
+    });
+}
+
+/* microbenchmark of the chain engine on one plain product C[M,N] = A·B (selectable operand layouts), for profiling */
+int dmrgx_selftest_gemm(dmrgx_ctx cx, dmrgx_int M, dmrgx_int N, dmrgx_int K, int a_k_contig, int b_k_contig, int nseg, int reps, double* ms,
+                        double* max_err) {
+    return guard([&] {
+        Ctx* ctx = C(cx);
+        BufRef A = std::make_shared<DevBuf>(ctx, (size_t)M * K * nseg * 8), B = std::make_shared<DevBuf>(ctx, (size_t)N * K * nseg * 8),
+               Cc = std::make_shared<DevBuf>(ctx, (size_t)M * N * 8);
+        dev::fill_random(ctx->st, A->as<double>(), M * K * nseg, 1);
+        dev::fill_random(ctx->st, B->as<double>(), N * K * nseg, 2);
+        Plan plan;
+        std::vector<Contribution> cs;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            Contribution c;
+            c.r0 = 0; c.c0 = 0; c.nr = (int)M; c.nc = (int)N;
+            c.seg = make_seg(dev::SEG_GEMM);
+            c.seg.A = A->as<double>() + (size_t)sgi * M * K; c.seg.B = B->as<double>() + (size_t)sgi * N * K; c.seg.K = (int)K;
+            if (a_k_contig) { c.seg.lda_m = K; c.seg.lda_k = 1; } else { c.seg.lda_m = 1; c.seg.lda_k = M; }
+            if (b_k_contig) { c.seg.ldb_n = K; c.seg.ldb_k = 1; } else { c.seg.ldb_n = 1; c.seg.ldb_k = N; }
+            cs.push_back(c);
+        }
+        emit_cells(plan, Cc->as<double>(), false, N, (int)M, (int)N, cs, true);
+        plan.upload(ctx);
+        plan.run(ctx);
+        dev::sync(ctx->st);
+        const double t0 = Trace::now();
+        for (int r = 0; r < reps; ++r) plan.run(ctx);
+        dev::sync(ctx->st);
+        *ms = (Trace::now() - t0) * 1e3 / std::max(1, reps);
+        /* spot check of one element against a host dot product */
+        std::vector<double> ha((size_t)M * K * nseg), hb((size_t)N * K * nseg), hc(1);
+        dev::d2h(ctx->st, ha.data(), A->p, ha.size() * 8); dev::d2h(ctx->st, hb.data(), B->p, hb.size() * 8);
+        const long long i = M / 3, j = N / 5;
+        dev::d2h(ctx->st, hc.data(), Cc->as<double>() + i * N + j, 8);
+        dev::sync(ctx->st);
+        double ref = 0;
+        for (int sgi = 0; sgi < nseg; ++sgi)
+            for (long long k = 0; k < K; ++k) {
+                const double a = a_k_contig ? ha[(size_t)sgi * M * K + i * K + k] : ha[(size_t)sgi * M * K + k * M + i];
+                const double b = b_k_contig ? hb[(size_t)sgi * N * K + j * K + k] : hb[(size_t)sgi * N * K + k * N + j];
+                ref += a * b;
+            }
+        *max_err = std::fabs(ref - hc[0]);
     });
 }
 

@@ -128,6 +128,7 @@ struct Plan {
     void run(Ctx* ctx, const double* x = nullptr, double* y = nullptr) const;
     /* useful work of the plan: 2*M*N*K of GEMM segments actually inside tile extents */
     double flops = 0;
+    double exec_flops = 0; /* what the kernel executes for them: padded to whole fragments and K chunks */
 };
 
 struct HShell {

@@ -182,7 +182,7 @@ void sync(Stream* st) { CUDA_OK(cudaStreamSynchronize(st->s)); }
 /* ================================================================================================
  *  chain_kernel
  * ============================================================================================== */
-constexpr int BM = 64, BN = 64, BK = 16, NTHREADS = 128;
+constexpr int BM = 64, BK = 16, NTHREADS = 128;
 constexpr int S_MK = BK + 4;  /* [m][k] layout row stride (20 ≡ 4 mod 16) */
 constexpr int S_KM = BM + 4;  /* [k][m] layout row stride (68 ≡ 4 mod 16) */
 constexpr int SMEM_TILE = (BM * S_MK > BK * S_KM) ? BM * S_MK : BK * S_KM; /* 1280 doubles */
@@ -205,8 +205,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 /* ---- operand staging ------------------------------------------------------------------------
  *  Each thread owns 8 elements of the A chunk and 8 of the B chunk.  Rows beyond the tile extent are
  *  CLAMPED to the last valid row (their products land in accumulator rows that are never stored), so
- *  the only predicate is the K tail, and the global pointers are bumped by a constant per chunk.
- *  Layout template parameters make every shared-memory offset an immediate.                       */
+ *  the only predicate is the K tail — carried by the zero-fill size operand of cp.async, one code path —
+ *  and the global pointers are bumped by a constant per chunk.  Layout template parameters make every
+ *  shared-memory offset an immediate.                                                             */
 template <bool MK> /* MK: operand contiguous along k -> smem [row][k]; else contiguous along row -> smem [k][row] */
 struct Stager {
     const double* base;  /* bumped by kstep per chunk */
@@ -238,23 +239,22 @@ struct Stager {
     }
     /* krem = K - k0 of this chunk (>= 1) */
     __device__ __forceinline__ void issue(double* sm, int krem) {
-        if (krem >= BK) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp_async8(sm + soff + i * SI, base + off[i], true);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool v = (MK ? k0 : k0 + 2 * i) < krem;
-                cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const bool v = (MK ? k0 : k0 + 2 * i) < krem;
+            cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
         }
         base += kstep;
     }
 };
 
-template <bool A_MK, bool B_NK, int NMI>
+/* One GEMM segment of a chain.  FULL: a 64×64 tile with a unit coefficient — every warp owns 4×4 fragments, no predicate
+   and no multiply in the inner loop (the plan folds the couplings into the right factors, so this is where the flops
+   are).  Otherwise the generic variant: fragment counts and the coefficient are runtime values.  Two variants per
+   operand layout keep the kernel small enough for the instruction caches. */
+template <bool A_MK, bool B_NK, bool FULL>
 __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
-                                             int tid, int rbase, int cbase, int g, int t, int nni) {
+                                             int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
     Stager<A_MK> sa;
     Stager<B_NK> sb;
     sa.init(sg.A + (long long)it.m0 * sg.lda_m, sg.lda_m, sg.lda_k, it.tm, tid);
@@ -286,17 +286,16 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
         const double* bs = Bs + cur * SMEM_TILE + b_base;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[NMI];
+            double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < NMI; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
+            for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                if (ni < nni) { /* warp-uniform branch; the coefficient rides on the B fragment (1 DMUL per 4 DMMA) */
-                    const double b = bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
+            for (int ni = 0; ni < 4; ++ni) b[ni] = FULL ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
 #pragma unroll
-                    for (int mi = 0; mi < NMI; ++mi) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b);
-                }
-            }
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+                    if (FULL || (mi < nmi && ni < nni)) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
         __syncthreads();
     }
@@ -305,14 +304,9 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
 template <bool A_MK, bool B_NK>
 __device__ __forceinline__ void gemm_dispatch(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                               int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
-    /* nmi is warp-uniform but differs between the two warp rows of an edge tile: every warp must still take part in
-       the staging and the barriers, so a warp without rows runs the 1-fragment variant on clamped (duplicate) rows */
-    switch (nmi) {
-        case 4: gemm_segment<A_MK, B_NK, 4>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
-        case 3: gemm_segment<A_MK, B_NK, 3>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
-        case 2: gemm_segment<A_MK, B_NK, 2>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nni); break;
-        default: gemm_segment<A_MK, B_NK, 1>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi > 0 ? nni : 0); break;
-    }
+    /* block-uniform choice: every warp of a 64×64 tile has 4×4 fragments */
+    if (it.tm == BM && it.tn == BM && sg.coef == 1.0) gemm_segment<A_MK, B_NK, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, 4, 4);
+    else gemm_segment<A_MK, B_NK, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __restrict__ items, const Segment* __restrict__ segs,
@@ -354,6 +348,28 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
                 if (b_nk) gemm_dispatch<false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
                 else gemm_dispatch<false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
             }
+        } else if (sg.type == SEG_AXPY) {
+            /* acc += coef * A(m,n): all of a thread's (up to 32) loads are issued before the first use */
+            const double* base = sg.A + (long long)(it.m0 + rbase + g) * sg.lda_m + (long long)(it.n0 + cbase + 2 * t) * sg.lda_k;
+            const long long sm8 = 8 * sg.lda_m, sn8 = 8 * sg.lda_k, sn1 = sg.lda_k;
+            double v[4][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const bool rok = mi < nmi && rbase + mi * 8 + g < tm;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = cbase + ni * 8 + 2 * t;
+                    const bool c0 = rok && ni < nni && col < tn, c1 = rok && ni < nni && col + 1 < tn;
+                    const double* q = base + mi * sm8 + ni * sn8;
+                    v[mi][ni][0] = c0 ? q[0] : 0.0;
+                    v[mi][ni][1] = c1 ? q[sn1] : 0.0;
+                }
+            }
+            const double coef = sg.coef;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] += coef * v[mi][ni][0]; acc[mi][ni][1] += coef * v[mi][ni][1]; }
         } else {
             /* slow-path segments: each thread updates the accumulator elements it owns */
 #pragma unroll

@@ -158,7 +158,9 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
                             raw[b].t.nr == raw[a].t.nr && raw[b].t.nc == raw[a].t.nc && raw[b].t.sr == raw[a].t.sr && raw[b].t.sc == raw[a].t.sc) {
                             same.push_back(b); used[b] = 1;
                         }
-                if (same.size() == 1) { bt[g][ir].push_back(raw[a]); touch(raw[a].t); continue; }
+                /* a lone factor is used in place unless it carries a coefficient: the GEMM inner loop is free of
+                   multiplies only for unit coefficients, so a·B is materialised too (one small axpy at plan time) */
+                if (same.size() == 1 && (raw[a].coef == 1.0 || !contiguous_dense(raw[a].t))) { bt[g][ir].push_back(raw[a]); touch(raw[a].t); continue; }
                 /* Σ_j a_j B_j materialised once (device axpy over the contiguous panels) */
                 const long long cnt = (long long)raw[a].t.nr * raw[a].t.nc;
                 BTile merged = raw[a];

@@ -103,17 +103,19 @@ void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Nc
             /* tile extents in units of 16 rows/cols (two 8-row DMMA fragments, one per warp row), spread as evenly as
                possible over ceil(units/4) tiles: every tile is 64 or 48 (or less, for small cells) wide, and the two
                warp rows / columns of a CTA carry the same number of fragments */
+            /* as many full 64-wide tiles as possible (they take the kernel's predicate-free path); the remainder is one
+               ragged tile, merged with the last full tile and halved when that makes two tiles of at most 64 and at least
+               40 (a sliver would waste a whole CTA on the fixed costs of a tile) */
             auto split = [](int len) {
                 std::vector<int> ext;
-                const int units = (len + 15) / 16;
-                const int ntile = (units + 3) / 4;
-                int left = len;
-                for (int i = 0; i < ntile; ++i) {
-                    const int u = units / ntile + (i < units % ntile ? 1 : 0);
-                    const int e = std::min(left, u * 16);
-                    ext.push_back(e);
-                    left -= e;
-                }
+                const int nfull = len / 64, rem = len % 64;
+                for (int i = 0; i < nfull; ++i) ext.push_back(64);
+                if (rem == 0) return ext;
+                if (nfull > 0 && rem < 24) {
+                    ext.pop_back();
+                    const int tot = 64 + rem, h = (((tot + 1) / 2) + 7) / 8 * 8;
+                    ext.push_back(h); ext.push_back(tot - h);
+                } else ext.push_back(rem);
                 return ext;
             };
             const std::vector<int> em = split(M), en = split(N);
@@ -146,6 +148,15 @@ void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Nc
                     it.tm = tm; it.tn = tn;
                     it.mode = 0;
                     double* dst = C + (long long)(r0 + m0) * ldc + (c0 + n0);
+                    {   /* FP64 tensor flops the kernel will EXECUTE for this tile: whole 8-row / 8-column fragments per warp half,
+                           whole 16-deep K chunks (the useful count is plan.flops) */
+                        auto frag = [](int t) { const int h = ((t + 15) >> 4) << 3; const int a = std::min(h, ((t + 7) / 8) * 8);
+                                                const int b = std::max(0, std::min(h, ((t - h + 7) / 8) * 8)); return a + b; };
+                        double kx = 0;
+                        for (int sgi = seg_begin; sgi < seg_end; ++sgi)
+                            if (plan.segs[sgi].type == dev::SEG_GEMM) kx += 16.0 * ((plan.segs[sgi].K + 15) / 16);
+                        plan.exec_flops += 2.0 * frag(tm) * frag(tn) * kx;
+                    }
                     if (nparts == 1) {
                         it.C = dst; it.ldc = ldc; it.c_in_y = c_in_y ? 1 : 0;
                         it.seg_begin = seg_begin; it.seg_end = seg_end;

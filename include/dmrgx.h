@@ -114,6 +114,10 @@ int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmr
 /* profiling aids: run only stage 1 (V = A·X panels) or stage 2 (Y = Σ V·Bᵀ) of an apply, and their useful flops */
 int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y);
 int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
+/* the FP64 tensor flops the two launches execute for them (tiles padded to whole DMMA fragments and K chunks) */
+int dmrgx_hshell_stage_exec_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
+/* plan introspection: per work item {tm, tn, segments, sum of K of its GEMM segments}; returns the item count */
+dmrgx_int dmrgx_hshell_plan_items(dmrgx_hshell h, int stage, dmrgx_int cap, dmrgx_int* out4);
 /* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, (all-gather,) apply, D2H, synchronous.  x and y are
    this rank's LOCAL rows, as VecGetArray returns them on the reference's MPI vectors — the whole vector on one GPU. */
 int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y);
@@ -158,6 +162,11 @@ int dmrgx_expect(dmrgx_hshell h1, const double* d_psi, double* value);
         Returns the number of terms (fills at most maxterms); bc: 0 open, 1 periodic; nsites < 0 = full lattice. ---- */
 dmrgx_int dmrgx_ham_terms(dmrgx_int Lx, dmrgx_int Ly, double J1, double Jz1, double J2, double Jz2, int bcx, int bcy, dmrgx_int nsites,
                           dmrgx_int maxterms, double* a, int* iop, dmrgx_int* isite, int* jop, dmrgx_int* jsite);
+
+/* ---- microbenchmark of the contraction engine on one plain product C[M,N] = Σ_seg A_seg·B_segᵀ (operand layouts selectable),
+        used by tools/ and the profiles; not part of the reference's surface ---- */
+int dmrgx_selftest_gemm(dmrgx_ctx ctx, dmrgx_int M, dmrgx_int N, dmrgx_int K, int a_k_contig, int b_k_contig, int nseg, int reps, double* ms,
+                        double* max_err);
 
 /* ---- device vectors (the Vec objects of the callers) ---- */
 int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out);
