@@ -252,7 +252,7 @@ struct Stager {
    and no multiply in the inner loop (the plan folds the couplings into the right factors, so this is where the flops
    are).  Otherwise the generic variant: fragment counts and the coefficient are runtime values.  Two variants per
    operand layout keep the kernel small enough for the instruction caches. */
-template <bool A_MK, bool B_NK, bool FULL>
+template <bool A_MK, bool B_NK, bool FULL, bool UNIT>
 __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                              int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
     Stager<A_MK> sa;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = FULL ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
+            for (int ni = 0; ni < 4; ++ni) b[ni] = UNIT ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -305,8 +305,10 @@ template <bool A_MK, bool B_NK>
 __device__ __forceinline__ void gemm_dispatch(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                               int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
     /* block-uniform choice: every warp of a 64×64 tile has 4×4 fragments */
-    if (it.tm == BM && it.tn == BM && sg.coef == 1.0) gemm_segment<A_MK, B_NK, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, 4, 4);
-    else gemm_segment<A_MK, B_NK, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+    if (sg.coef == 1.0) {
+        if (it.tm == BM && it.tn == BM) gemm_segment<A_MK, B_NK, true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, 4, 4);
+        else gemm_segment<A_MK, B_NK, false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+    } else gemm_segment<A_MK, B_NK, false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __restrict__ items, const Segment* __restrict__ segs,
