@@ -119,6 +119,10 @@ void multidot(Stream*, const double* V, long long ldv, int nvec, const double* w
    if d_nrm2: *d_nrm2 = ||w_new||²  */
 void multiaxpy(Stream*, const double* V, long long ldv, int nvec, const double* d_coef, double* w, long long n, double* d_dots2,
                double* d_nrm2);
+/* One fused Gram-Schmidt pass over the basis (a single read of V, deterministic reductions finished by the last block, no
+   host involvement):   if d_coef:  w -= Σ_i d_coef[i]·V_i   (in place);   then, on the updated w,
+   if d_dots: d_dots[i] = V_i·w (i < nvec);   if d_nrm2: *d_nrm2 = w·w.   nvec <= 40. */
+void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long long n, const double* d_coef, double* d_dots, double* d_nrm2);
 /* v = w / sqrt(*d_nrm2) */
 void scale_inv_norm(Stream*, const double* w, const double* d_nrm2, double* v, long long n);
 /* in place: V_a <- Σ_i S[i*kk+a] V_i  (i < ncv, a < kk), S on the device */

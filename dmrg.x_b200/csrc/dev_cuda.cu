@@ -52,6 +52,7 @@ struct Stream {
     bool own = false;
     cusolverDnHandle_t solver = nullptr;
     double* partials = nullptr; /* deterministic two-stage reductions */
+    unsigned int* ticket = nullptr; /* "last block finishes the reduction" counter of gs_pass */
     int* info = nullptr;
     void* solver_work = nullptr;
     size_t solver_work_bytes = 0;
@@ -96,6 +97,8 @@ int init(int device, void* user_stream, Stream** out) {
         st->num_sms = prop.multiProcessorCount;
         CUDA_OK(cudaMalloc(&st->partials, sizeof(double) * RED_BLOCKS * RED_MAXVEC));
         CUDA_OK(cudaMalloc(&st->info, sizeof(int) * 4));
+        CUDA_OK(cudaMalloc(&st->ticket, sizeof(unsigned int)));
+        CUDA_OK(cudaMemset(st->ticket, 0, sizeof(unsigned int)));
         if (cusolverDnCreate(&st->solver) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
         cusolverDnSetStream(st->solver, st->s);
         *out = st;
@@ -122,6 +125,7 @@ void destroy(Stream* st) {
     for (auto& kv : st->free_lists) for (void* q : kv.second) cudaFree(q);
     for (auto& kv : st->live) cudaFree(kv.first);
     cudaFree(st->partials);
+    cudaFree(st->ticket);
     cudaFree(st->info);
     if (st->own) cudaStreamDestroy(st->s);
     delete st;
@@ -552,6 +556,83 @@ void multiaxpy(Stream* st, const double* V, long long ldv, int nvec, const doubl
     }
     if (d_dots2) multidot(st, V, ldv, nvec, w, n, d_dots2);
     if (d_nrm2) dot(st, w, w, n, d_nrm2);
+}
+
+/* ---- fused Gram-Schmidt pass -------------------------------------------------------------------
+ *  HBM-bound: one streaming read of nvec basis vectors (+ one read / optional write of w) per pass.  Each thread keeps
+ *  its basis elements in registers between the update and the dot products, so the "reorthogonalise and measure" step
+ *  costs one pass instead of two.  Block partial sums go to a scratch table; the block that draws the last ticket adds
+ *  them in block order (a fixed order: bit-reproducible, no floating-point atomics). */
+template <int NV>
+__global__ void __launch_bounds__(256) gs_pass_kernel(const double* __restrict__ V, long long ldv, int nvec, double* __restrict__ w, long long n,
+                                                      const double* __restrict__ coef, double* __restrict__ dots, double* __restrict__ nrm2,
+                                                      double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    __shared__ double c[NV];
+    __shared__ double sh[NV + 1][8];
+    __shared__ bool last;
+    if (threadIdx.x < NV) c[threadIdx.x] = (coef && threadIdx.x < nvec) ? coef[threadIdx.x] : 0.0;
+    __syncthreads();
+    double s[NV + 1];
+#pragma unroll
+    for (int i = 0; i <= NV; ++i) s[i] = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        double v[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = i < nvec ? V[i * ldv + q] : 0.0;
+        double wq = w[q];
+        if (coef) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) wq -= c[i] * v[i];
+            w[q] = wq;
+        }
+        if (dots) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) s[i] += v[i] * wq;
+        }
+        s[NV] += wq * wq;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i <= NV; ++i) {
+        const double r = warp_sum(s[i]);
+        if (lane == 0) sh[i][wid] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NV) {
+        double r = 0.0;
+        for (int k = 0; k < 8; ++k) r += sh[threadIdx.x][k];
+        partials[(long long)blockIdx.x * (NV + 1) + threadIdx.x] = r;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    /* the last block: warp `wid` sums columns wid, wid+8, ... over all blocks in block order */
+    for (int i = wid; i <= NV; i += 8) {
+        double r = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) r += partials[(long long)b * (NV + 1) + i];
+        r = warp_sum(r);
+        if (lane == 0) {
+            if (i < NV) { if (dots && i < nvec) dots[i] = r; }
+            else if (nrm2) *nrm2 = r;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+void gs_pass(Stream* st, const double* V, long long ldv, int nvec, double* w, long long n, const double* d_coef, double* d_dots, double* d_nrm2) {
+    if (nvec > RED_MAXVEC - 1) throw std::runtime_error("gs_pass: too many basis vectors");
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+#define GS_LAUNCH(NV) gs_pass_kernel<NV><<<blocks, 256, 0, st->s>>>(V, ldv, nvec, w, n, d_coef, d_dots, d_nrm2, st->partials, st->ticket)
+    if (nvec <= 4) GS_LAUNCH(4);
+    else if (nvec <= 8) GS_LAUNCH(8);
+    else if (nvec <= 12) GS_LAUNCH(12);
+    else if (nvec <= 17) GS_LAUNCH(17);
+    else if (nvec <= 24) GS_LAUNCH(24);
+    else GS_LAUNCH(39);
+#undef GS_LAUNCH
+    LAUNCH_CHECK();
 }
 
 __global__ void scale_inv_norm_kernel(const double* __restrict__ w, const double* __restrict__ nrm2, double* __restrict__ v, long long n) {

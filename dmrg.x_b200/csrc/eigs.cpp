@@ -64,14 +64,16 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     BufRef basis = std::make_shared<DevBuf>(ctx, (size_t)(ld + 1) * std::max<long long>(1, N) * 8);
     BufRef wbuf = std::make_shared<DevBuf>(ctx, (size_t)std::max<long long>(1, N) * 8);
     BufRef xfull = dist ? std::make_shared<DevBuf>(ctx, (size_t)NG * 8) : nullptr;
-    BufRef scal = std::make_shared<DevBuf>(ctx, (size_t)(2 * (ld + 2) + ld * ld) * 8);
+    /* coefficient table: one row per Lanczos step of a restart cycle = {pass-1 coefficients (ld+1), pass-2 coefficients
+       (ld+1), ||w||^2}.  It is read back ONCE per cycle: the steps of a cycle are queued without any host round trip. */
+    const int RW = 2 * (ld + 1) + 1;
+    BufRef scal = std::make_shared<DevBuf>(ctx, (size_t)(ld * RW + 2 + ld * ld) * 8);
     double* V = basis->as<double>();
     double* w = wbuf->as<double>();
-    double* d_h = scal->as<double>();            /* ld+1 coefficients, pass 1 */
-    double* d_h2 = d_h + (ld + 1);               /* pass 2 */
-    double* d_nrm2 = d_h2 + (ld + 1);
+    double* d_tab = scal->as<double>();
+    double* d_nrm2 = d_tab + (size_t)ld * RW;
     double* d_S = d_nrm2 + 2;
-    std::vector<double> hh(2 * (ld + 1) + 1);
+    std::vector<double> hh((size_t)ld * RW);
     std::vector<double> T((size_t)ld * ld, 0.0);
 
     Trace tr(ctx, "eigs");
@@ -93,25 +95,32 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
                 hshell_apply(H, V + (size_t)j * N, w);
             }
             stats.nmatvec++;
-            /* classical Gram-Schmidt against the whole basis, twice; coefficients never leave the device
-               except as the ncv+2 numbers the projected matrix needs */
-            dev::multidot(st, V, N, j + 1, w, N, d_h);
+            /* classical Gram-Schmidt against the whole basis, twice, as three fused passes (dots | update+dots | update+norm);
+               the coefficients stay on the device until the end of the cycle */
+            double* d_h = d_tab + (size_t)j * RW;
+            double* d_h2 = d_h + (ld + 1);
+            double* d_n = d_h2 + (ld + 1);
+            dev::gs_pass(st, V, N, j + 1, w, N, nullptr, d_h, nullptr);
             dev::allreduce_sum(st, d_h, j + 1);
-            dev::multiaxpy(st, V, N, j + 1, d_h, w, N, d_h2, nullptr);
+            dev::gs_pass(st, V, N, j + 1, w, N, d_h, d_h2, nullptr);
             dev::allreduce_sum(st, d_h2, j + 1);
-            dev::multiaxpy(st, V, N, j + 1, d_h2, w, N, nullptr, d_nrm2);
-            dev::allreduce_sum(st, d_nrm2, 1);
-            dev::d2h(st, hh.data(), d_h, (size_t)(2 * (ld + 1) + 1) * 8);
-            dev::sync(st);
+            dev::gs_pass(st, V, N, j + 1, w, N, d_h2, nullptr, d_n);
+            dev::allreduce_sum(st, d_n, 1);
+            dev::scale_inv_norm(st, w, d_n, V + (size_t)(j + 1) * N, N);
+        }
+        dev::d2h(st, hh.data() + (size_t)k * RW, d_tab + (size_t)k * RW, (size_t)(nc - k) * RW * 8);
+        dev::sync(st);
+        for (int j = k; j < nc; ++j) {
+            const double* r = hh.data() + (size_t)j * RW;
             for (int i = 0; i <= j; ++i) {
-                const double c = hh[i] + hh[(ld + 1) + i];
+                const double c = r[i] + r[(ld + 1) + i];
                 T[(size_t)i * ld + j] = c;
                 T[(size_t)j * ld + i] = c;
             }
-            const double b = std::sqrt(std::max(0.0, hh[2 * (ld + 1)]));
+            const double b = std::sqrt(std::max(0.0, r[2 * (ld + 1)]));
             beta_last = b;
-            if (b < 1e-14) { nc = j + 1; invariant = true; break; }
-            dev::scale_inv_norm(st, w, d_nrm2, V + (size_t)(j + 1) * N, N);
+            /* invariant subspace reached at step j: what was queued after it worked on a null direction and is ignored */
+            if (!(b >= 1e-14)) { nc = j + 1; invariant = true; break; }
         }
         std::vector<double> Tm((size_t)nc * nc), ev, S;
         for (int i = 0; i < nc; ++i) for (int j = 0; j < nc; ++j) Tm[(size_t)i * nc + j] = T[(size_t)i * ld + j];

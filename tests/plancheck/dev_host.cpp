@@ -121,6 +121,12 @@ void multiaxpy(Stream* st, const double* V, long long ldv, int nvec, const doubl
     if (dots2) multidot(st, V, ldv, nvec, w, n, dots2);
     if (nrm2) dot(st, w, w, n, nrm2);
 }
+void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long long n, const double* coef, double* dots, double* nrm2) {
+    ++g_launches;
+    if (coef) for (int i = 0; i < nvec; ++i) for (long long q = 0; q < n; ++q) w[q] -= coef[i] * V[i * ldv + q];
+    if (dots) for (int i = 0; i < nvec; ++i) { double s = 0; for (long long q = 0; q < n; ++q) s += V[i * ldv + q] * w[q]; dots[i] = s; }
+    if (nrm2) { double s = 0; for (long long q = 0; q < n; ++q) s += w[q] * w[q]; *nrm2 = s; }
+}
 void scale_inv_norm(Stream*, const double* w, const double* nrm2, double* v, long long n) {
     ++g_launches;
     const double inv = 1.0 / std::sqrt(*nrm2);
