@@ -142,3 +142,44 @@ def oracle_side(O, wl):
     enl = O.kron_eye(b, O.Block.single_site(), wl.terms_enl)
     kb = O.KronBlocks(enl, enl, [0.0])
     return enl, kb
+
+
+class ExactChainWorkload:
+    """The sparse-sector case of the north star: UN-truncated blocks.  An open Heisenberg chain of 2*nhalf sites cut in the
+    middle, both halves represented exactly (2^nhalf states, operators with O(1) non-zeros per row).  The operators are
+    handed over as CSR with global column indices — what a maintainer of the reference passes from MatGetRow (route B of
+    INTEGRATION.md) — so the library stores them as CSR / scaled-identity tiles and H*psi runs on the sparse segments of
+    the chain kernel instead of the FP64 tensor path.  Bound: HBM."""
+
+    def __init__(self, P, ctx, nhalf=12):
+        ham = CONFIGS["heis_chain24"]
+        self.P, self.ctx, self.nhalf = P, ctx, nhalf
+        Lx = 2 * nhalf
+        T = lambda n: P.HamiltonianTerms(Lx, 1, ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, ham["bcx"], ham["bcy"])
+        site = P.Block.SingleSite(ctx)
+        blk = P.Block.SingleSite(ctx)
+        for n in range(2, nhalf + 1):
+            blk = P.KronEye_Explicit(blk, site, T(n))
+        # round trip through host CSR: the upload path classifies every sector block by fill (dense / CSR / identity runs)
+        qn, sz = blk.sectors()
+        ctx.set_dense_threshold(0.125)
+        up = P.Block.Initialize(ctx, nhalf, qn, sz)
+        nnz = 0
+        for i in range(nhalf):
+            for op in (P.OpSz, P.OpSp):
+                rp, ci, vv = blk.get_operator(op, i)
+                up.set_operator(op, i, rp, ci, vv)
+        rp, ci, vv = blk.get_operator(P.OpH, 0)
+        nnz = len(vv)
+        up.set_operator(P.OpH, 0, rp, ci, vv)
+        self.h_nnz_per_row = nnz / float(up.NumStates())
+        self.blk = up
+        self.terms = T(Lx)
+        self.kron = P.KronBlocks(up, up, [0.0])
+        self.shell = self.kron.KronSumConstruct(self.terms)
+        self.n = self.kron.NumStates()
+
+    def random_state(self, seed=1):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(self.n)
+        return x / np.linalg.norm(x)

@@ -74,7 +74,7 @@ struct Stream {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
 };
-constexpr int SOLVER_LANES = 8;
+constexpr int SOLVER_LANES = 16;
 
 constexpr int RED_BLOCKS = 592; /* 148 SMs × 4 resident CTAs */
 constexpr int RED_MAXVEC = 40;
@@ -147,11 +147,13 @@ static size_t size_class(size_t bytes) {
 }
 void* malloc_bytes(Stream* st, size_t bytes) {
     const size_t cls = size_class(bytes);
-    auto f = st->free_lists.find(cls);
-    if (f != st->free_lists.end() && !f->second.empty()) {
+    /* best fit among the cached blocks of this class or up to twice as large: sizes drift from step to step in a sweep, and
+       a cudaMalloc (milliseconds, device-wide synchronisation) per new class showed up as the jitter of the rotation phase */
+    for (auto f = st->free_lists.lower_bound(cls); f != st->free_lists.end() && f->first <= 2 * cls; ++f) {
+        if (f->second.empty()) continue;
         void* p = f->second.back();
         f->second.pop_back();
-        st->live[p] = cls;
+        st->live[p] = f->first;
         return p;
     }
     void* p = nullptr;

@@ -152,3 +152,16 @@ def test_error_codes(P, ctx):
     with pytest.raises(P.DmrgxError) as e:
         b.set_operator(P.OpSz, 7, [0] * 9, [], [])
     assert e.value.code == 63
+
+
+def test_exact_chain_sparse_workload_ground_state(P, ctx):
+    """The sparse-sector path on the GPU (CSR / identity tiles, no tensor work): exact 8-site halves of the 16-site open
+    Heisenberg chain; E0 from exact diagonalisation."""
+    import bench_workload as W
+    sw = W.ExactChainWorkload(P, ctx, 8)
+    assert sw.n == 12870
+    e, psi, st = sw.shell.EPSSolve(tol=1e-12)
+    assert st["converged"] and abs(e - (-6.911737145575)) < 1e-9
+    x = sw.random_state(4); y = sw.random_state(5)
+    Hx = sw.shell.MatMult_host(x); Hy = sw.shell.MatMult_host(y)
+    assert abs(y @ Hx - x @ Hy) < 1e-12

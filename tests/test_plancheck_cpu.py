@@ -143,3 +143,13 @@ def test_no_device_no_fallback():
     lib = C.CDLL(P.LIB_PATH)
     h = C.c_void_p()
     assert lib.dmrgx_ctx_create(0, None, C.byref(h)) == 100
+
+
+def test_exact_chain_sparse_workload_ground_state(P, ctx):
+    """Un-truncated (sparse / identity-tile) blocks uploaded as CSR: the shell of the 12-site open Heisenberg chain cut in
+    the middle must have the exact ground-state energy of SURVEY.md §8c."""
+    import bench_workload as W
+    sw = W.ExactChainWorkload(P, ctx, 6)
+    assert sw.n == 924
+    e, psi, st = sw.shell.EPSSolve(tol=1e-12)
+    assert st["converged"] and abs(e - (-5.142090632841)) < 1e-9
