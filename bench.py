@@ -25,6 +25,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the two chain_kernel launches of one apply, from the ncu capture summarised
+# in profiles/r1_chain_kernel.md (same command line, same build)
+NCU_TRAFFIC_BYTES = {("j1j2_12x6", 2048): 1.364e9}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -35,6 +40,7 @@ def parse():
     ap.add_argument("--m", type=int, default=2048)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep measurement (DMRG-SquareLattice.x on configs[1])")
     return ap.parse_args()
 
 
@@ -306,6 +312,31 @@ def main():
         except Exception as exc:
             sparse = {"error": repr(exc)}
 
+    # seconds per sweep (the metric's second half) through the reference-named executable on BASELINE configs[1]
+    # (Heisenberg 8x4 cylinder, m = 512, one B200); the 12x6 m = 2048 sweep takes minutes and is recorded in profiles/
+    sweep = {}
+    exe = os.path.join(ROOT, "dmrg.x_b200", "DMRG-SquareLattice.x")
+    if world == 1 and rank == 0 and not args.no_sweep and os.path.exists(exe):
+        try:
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                cmd = [exe, "-Lx", "8", "-Ly", "4", "-heisenberg", "1", "-mwarmup", "64", "-msweeps", "256,512,512", "-data_dir", td + "/", "-do_correlators", "0",
+                       "-device", str(local)]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-500:])
+                run = json.load(open(os.path.join(td, "DMRGRun.json")))
+                steps = json.load(open(os.path.join(td, "DMRGSteps.json")))
+                tim = json.load(open(os.path.join(td, "Timings.json")))
+                last = [t for t, srow in zip(tim["table"], steps["table"]) if srow[2] == max(x[2] for x in steps["table"])]
+                names = tim["headers"][1:]
+                sweep = {"config": "heis_8x4 cylinder (BASELINE configs[1]) -mwarmup 64 -msweeps 256,512,512, one GPU, default -H_eps_tol 1e-8",
+                         "m": 512, "seconds_per_sweep": run["Sweeps"]["Seconds"][-1], "steps_per_sweep": len(last),
+                         "phases_s": {n: float(sum(row[i + 1] for row in last)) for i, n in enumerate(names)},
+                         "energy": steps["table"][-1][-1], "matvecs_total": run["NumMatVecs"]}
+        except Exception as exc:
+            sweep = {"error": repr(exc)}
+
     # e2e: the reference-facing call with HOST buffers, copies inside the timed region
     hx = torch.from_numpy(wl.random_state(2)[rb:re_].copy()).pin_memory()   # this rank's local rows, like VecGetArray
     hy = torch.empty(re_ - rb, dtype=torch.float64).pin_memory()
@@ -336,12 +367,15 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s", "frac": achieved / peak_fp64,
-                     "traffic": None, "kernel": "chain_kernel (FP64 DMMA), 2 launches per apply",
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.config, args.m)) if world == 1 else None,
+                     "traffic_source": "profiles/r1_chain_kernel.md (ncu --set full, dram read+write of the two launches of one apply)",
+                     "kernel": "chain_kernel (FP64 DMMA), 2 launches per apply",
                      "peak_source": "cuBLAS DGEMM %d^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)" % 6144,
                      "stage_ms": [t1, t2], "stage_flops": [f1, f2],
                      "hbm_frac_of_%s_peak" % peaks_kind: (st["alg_bytes"] / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"]},
         "lanczos": lz,
         "sparse_sector": sparse,
+        "sweep": sweep,
         "alg": {"bytes_per_apply": st["alg_bytes_global"], "flops_per_apply": st["alg_flops_global"], "rank0_flops": st["alg_flops"], "D": n,
                 "tiles": [st["tiles_stage1"], st["tiles_stage2"]]},
     }

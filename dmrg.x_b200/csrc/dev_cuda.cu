@@ -755,6 +755,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -769,7 +771,7 @@ NcclApi& nccl() {
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) { g_err = std::string("cannot load NCCL: ") + dlerror(); return api; }
 #define BIND(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name); if (!api.name) { g_err = "NCCL symbol nccl" #name " missing"; return api; }
-    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(AllReduce) BIND(Broadcast) BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(AllReduce) BIND(Broadcast) BIND(Send) BIND(Recv) BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
 #undef BIND
     api.ok = true;
     return api;
@@ -813,12 +815,18 @@ void allreduce_sum(Stream* st, double* d_buf, long long n) {
     if (st->world <= 1 || n <= 0) return;
     NCCL_OK(nccl().AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, st->comm, st->s));
 }
+/* Ragged in-place all-gather as ONE group of point-to-point transfers: every rank sends its own range to each peer and
+   receives each peer's range straight into place.  Through NVSwitch all pairs run at full bandwidth at once, and the
+   group is a single NCCL kernel — a chain of per-root broadcasts cost 0.1-0.3 ms at 4-8 ranks for 15 MB. */
 void allgatherv(Stream* st, double* d_buf, const long long* off) {
     if (st->world <= 1) return;
+    const long long mine = off[st->rank + 1] - off[st->rank];
     NCCL_OK(nccl().GroupStart());
-    for (int r = 0; r < st->world; ++r) {
-        const long long cnt = off[r + 1] - off[r];
-        if (cnt > 0) NCCL_OK(nccl().Broadcast(d_buf + off[r], d_buf + off[r], (size_t)cnt, ncclDouble, r, st->comm, st->s));
+    for (int d = 1; d < st->world; ++d) {
+        const int to = (st->rank + d) % st->world, from = (st->rank - d + st->world) % st->world;
+        if (mine > 0) NCCL_OK(nccl().Send(d_buf + off[st->rank], (size_t)mine, ncclDouble, to, st->comm, st->s));
+        const long long cnt = off[from + 1] - off[from];
+        if (cnt > 0) NCCL_OK(nccl().Recv(d_buf + off[from], (size_t)cnt, ncclDouble, from, st->comm, st->s));
     }
     NCCL_OK(nccl().GroupEnd());
 }
