@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--m", type=int, default=2048)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--from-disk", default=None, help="BASELINE configs[4]: a Sweep_*/ directory of saved blocks (InitializeFromDisk layout) "
+                    "to take the superblock from instead of the synthetic one")
     ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep measurement (DMRG-SquareLattice.x on configs[1])")
     return ap.parse_args()
 
@@ -224,7 +226,9 @@ def main():
     torch.cuda.set_stream(tstream)
     assert tstream.cuda_stream != 0
     ctx = P.Context(local, tstream.cuda_stream, rank, world, uid)
-    wl = W.Workload(P, ctx, args.config, m=args.m)
+    wl = W.DiskWorkload(P, ctx, args.config, args.from_disk) if args.from_disk else W.Workload(P, ctx, args.config, m=args.m)
+    if args.from_disk:
+        args.m = wl.m
     H = wl.shell
     st = H.stats()
     n = wl.n
@@ -358,7 +362,7 @@ def main():
     line = {
         "metric": "superblock H*psi algorithmic GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64", "data": "blocks read from disk (InitializeFromDisk layout)" if args.from_disk else "synthetic",
         "config": {"workload": "%s m=%d sweep-midpoint superblock H*psi, D=%d, T=%d shell terms" % (args.config, args.m, n, st["nterms"]),
                    "l2": "operator panels (%.0f MB) exceed the 126 MB L2, no flush needed" % ((st["alg_bytes_global"] - 16 * n) / 1e6),
                    "parallelism": ("superblock rows sharded over %d GPUs (cuts %s), NCCL all-gather of psi per apply" % (world, cuts.tolist()))
@@ -379,7 +383,7 @@ def main():
         "alg": {"bytes_per_apply": st["alg_bytes_global"], "flops_per_apply": st["alg_flops_global"], "rank0_flops": st["alg_flops"], "D": n,
                 "tiles": [st["tiles_stage1"], st["tiles_stage2"]]},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.from_disk:
         try:
             line["cpu_baseline"] = cpu_baseline(wl, args.cpu_baseline_seconds)
         except Exception as exc:  # the baseline is reported, never required for the GPU number

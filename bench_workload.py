@@ -8,6 +8,8 @@ exactly what a maintainer of the reference would hand over from MatGetRow — an
 (through dmrgx_block_set_operator) and, for parity tests and the CPU baseline only, to the oracle.
 Only the operators the Hamiltonian terms of the step touch are filled; the other sites get empty operators.
 """
+import os
+
 import numpy as np
 
 SEED = 20261018
@@ -183,3 +185,25 @@ class ExactChainWorkload:
         rng = np.random.default_rng(seed)
         x = rng.standard_normal(self.n)
         return x / np.linalg.norm(x)
+
+
+class DiskWorkload(Workload):
+    """BASELINE.json configs[4]: the isolated H*psi on blocks read from disk (InitializeFromDisk layout) — a Sweep_*/ directory
+    written by the reference or by `DMRG-SquareLattice.x -scratch_dir`: the sweep-midpoint superblock of its Sys_{N/2-2} block."""
+
+    def __init__(self, P, ctx, config, sweep_dir):
+        self.P, self.ctx, self.config = P, ctx, config
+        ham = CONFIGS[config]
+        self.ham = ham
+        N = ham["Lx"] * ham["Ly"]
+        self.nsites_blk = N // 2 - 1
+        T = lambda n: P.HamiltonianTerms(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, ham["bcx"], ham["bcy"])
+        self.terms_enl, self.terms = T(self.nsites_blk + 1), T(N)
+        self.blk = P.Block.InitializeFromDisk(ctx, os.path.join(sweep_dir, "Sys_%09d" % (self.nsites_blk - 1)))
+        assert self.blk.NumSites() == self.nsites_blk
+        self.m = self.blk.NumStates()
+        self.site = P.Block.SingleSite(ctx)
+        self.enl = P.KronEye_Explicit(self.blk, self.site, self.terms_enl)
+        self.kron = P.KronBlocks(self.enl, self.enl, [0.0])
+        self.shell = self.kron.KronSumConstruct(self.terms)
+        self.n = self.kron.NumStates()

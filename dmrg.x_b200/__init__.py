@@ -196,6 +196,40 @@ class Block:
         _chk(lib().dmrgx_block_single_site(ctx.h, int(spin_twice), C.byref(h)))
         return Block(ctx, h)
 
+    @staticmethod
+    def InitializeFromDisk(ctx, block_path):
+        """InitializeFromDisk(comm, block_path) — src/DMRGBlock.cpp:214-372: BlockInfo.dat, QuantumNumbers.dat and the PETSc
+        binary AIJ files Sz_%09d.mat / Sp_%09d.mat / H_000000000.mat (big-endian classid 1211216, M, N, nz, row lengths,
+        columns, values) of a block directory written by the reference or by DMRG-SquareLattice.x -scratch_dir."""
+        if not block_path.endswith("/"):
+            block_path += "/"
+        info = dict(l.split()[:2] for l in open(block_path + "BlockInfo.dat") if l.strip())
+        ib = int(info["NumBytesPetscInt"])
+        if int(info["NumBytesPetscScalar"]) != 8 or int(info["PetscUseComplex"]) != 0 or ib not in (4, 8):
+            raise DmrgxError(1, "incompatible BlockInfo.dat in " + block_path)
+        rows = [l.split() for l in open(block_path + "QuantumNumbers.dat") if l.strip()]
+        blk = Block.Initialize(ctx, int(info["NumSites"]), [float(q) for _, q in rows], [int(s) for s, _ in rows])
+        it = np.dtype(">i4" if ib == 4 else ">i8")
+
+        def load(name, isite):
+            raw = open("%s%s_%09d.mat" % (block_path, name, isite), "rb").read()
+            hdr = np.frombuffer(raw, it, 4)
+            if hdr[0] != 1211216 or hdr[1] != blk.NumStates() or hdr[2] != blk.NumStates():
+                raise DmrgxError(62, "not a PETSc binary matrix of this block: %s_%09d.mat" % (name, isite))
+            M, nz = int(hdr[1]), int(hdr[3])
+            off = 4 * ib
+            rowlen = np.frombuffer(raw, it, M, off).astype(np.int64); off += M * ib
+            col = np.frombuffer(raw, it, nz, off).astype(np.int64); off += nz * ib
+            val = np.frombuffer(raw, ">f8", nz, off).astype(np.float64)
+            return np.concatenate([[0], np.cumsum(rowlen)]), col, val
+        for i in range(blk.NumSites()):
+            blk.set_operator(OpSz, i, *load("Sz", i))
+            blk.set_operator(OpSp, i, *load("Sp", i))
+        if os.path.exists("%sH_%09d.mat" % (block_path, 0)):
+            blk.set_operator(OpH, 0, *load("H", 0))
+        _chk(blk.CheckOperatorBlocks())
+        return blk
+
     def set_operator(self, op, isite, rowptr, col, val):
         rowptr = _l(rowptr); col = _l(col); val = _d(val)
         _chk(lib().dmrgx_block_set_operator(self.h, int(op), LL(isite), _p(rowptr), _p(col), _p(val)))

@@ -87,6 +87,8 @@ public:
     PetscErrorCode EnsureSaved() { return 0; }
     PetscErrorCode EnsureRetrieved() { return 0; }
     PetscErrorCode InitializeSave(const std::string&) { return 0; }
+    /** InitializeFromDisk(comm, block_path): src/DMRGBlock.cpp:214-372 — implemented in DMRGBlockIO.hpp (BlockIO::Load) */
+    PetscErrorCode InitializeFromDisk(const MPI_Comm&, const std::string& block_path);
     PetscErrorCode SetDiskStorage(const std::string&, const std::string&) { return 0; }
     /** src/DMRGBlock.cpp:825-887 */
     PetscErrorCode Destroy() { h.reset(); init = PETSC_FALSE; num_sites = num_states = 0; return 0; }

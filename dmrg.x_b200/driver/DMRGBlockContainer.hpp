@@ -16,6 +16,7 @@
 #include <iostream>
 #include <set>
 
+#include "DMRGBlockIO.hpp"
 #include "DMRGKron.hpp"
 
 /** include/DMRGBlockContainer.hpp:21-27 */
@@ -62,8 +63,30 @@ public:
         PetscOptions& o = PetscOptions::DB();
         PetscErrorCode ierr;
         std::string path; PetscBool set = PETSC_FALSE;
-        o.GetString("-restart_dir", path, &set);
-        if (set) SETERRQ(mpi_comm, PETSC_ERR_SUP, "-restart_dir: blocks stay resident in HBM, the on-disk block format is not written yet");
+        /* -restart_dir: the directory of a previous run's scratch; continue from its last Sweep_* with a valid Sweep.dat (:286-347) */
+        o.GetString("-restart_dir", path, &restart);
+        if (restart) {
+            restart_dir = path;
+            if (restart_dir.back() != '/') restart_dir += "/";
+            PetscInt ridx = 0;
+            auto exists = [](const std::string& f) { std::ifstream t(f.c_str()); return (bool)t; };
+            while (ridx < MAX_SWEEP_IDX && !exists(restart_dir + SweepDir(ridx) + "Sweep.dat")) ++ridx;
+            if (ridx == MAX_SWEEP_IDX) SETERRQ1(mpi_comm, 1, "No Sweep directory was found in %s", restart_dir.c_str());
+            while (ridx < MAX_SWEEP_IDX && exists(restart_dir + SweepDir(ridx + 1) + "Sweep.dat")) ++ridx;
+            restart_dir = restart_dir + SweepDir(ridx);
+            { /* the Hamiltonian of the previous run (Hamiltonian.dat is an options file) */
+                std::ifstream in((restart_dir + "Hamiltonian.dat").c_str());
+                if (!in) SETERRQ1(mpi_comm, 1, "cannot read %sHamiltonian.dat", restart_dir.c_str());
+                std::stringstream ss; ss << in.rdbuf();
+                o.InsertString(ss.str());
+            }
+            std::map<std::string, PetscInt> d;
+            { std::ifstream in((restart_dir + "Sweep.dat").c_str()); for (std::string k; in >> k;) { PetscInt v; in >> v; d[k] = v; } }
+            for (const char* k : {"GlobIdx", "LoopIdx", "num_sys_blocks", "sys_ninit"}) if (!d.count(k)) SETERRQ1(mpi_comm, 1, "Sweep.dat: %s not found.", k);
+            GlobIdx = d["GlobIdx"]; LoopIdx = d["LoopIdx"] + 1; num_sys_blocks = d["num_sys_blocks"]; sys_ninit = d["sys_ninit"];
+            std::cout << "WARNING:\nThe following variables have been forcefully set:\n  GlobIdx " << GlobIdx << "\n  LoopIdx " << LoopIdx
+                      << "\n  num_sys_blocks " << num_sys_blocks << "\n  sys_ninit " << sys_ninit << std::endl;
+        }
 
         ierr = Ham.SetFromOptions(); CHKERRQ(ierr);
         ierr = SingleSite.Initialize(mpi_comm, 1, PETSC_DEFAULT); CHKERRQ(ierr);
@@ -84,6 +107,12 @@ public:
         o.GetString("-scratch_dir", scratch_dir, &set);
         if (!set) { scratch_dir = "./scratch_dir/"; }
         if (scratch_dir.back() != '/') scratch_dir += '/';
+        /* Blocks stay in HBM during a run; with an explicit -scratch_dir (or -save_blocks 1) every completed warm-up / sweep is
+           checkpointed to Sweep_%09d/Sys_%09d/ in the reference's on-disk format so that -restart_dir can pick it up. */
+        do_save_blocks = set;
+        o.GetBool("-save_blocks", &do_save_blocks, NULL);
+        { PetscInt v = io_int_bytes; o.GetInt("-petsc_int_bytes", &v, NULL); io_int_bytes = (int)v; }
+        if (io_int_bytes != 4 && io_int_bytes != 8) SETERRQ(mpi_comm, 1, "-petsc_int_bytes must be 4 or 8");
         std::string data_dir;
         o.GetString("-data_dir", data_dir, &set);
         if (!set) data_dir = "./data_dir/";
@@ -190,9 +219,22 @@ public:
     PetscErrorCode Warmup() {
         if (!init) SETERRQ(mpi_comm, 1, "DMRGBlockContainer object not initialized. Call Initialize() first.");
         if (dry_run) return 0;
-        if (mwarmup == 0) { std::cout << "WARNING: Nothing left to do since mwarmup is zero." << std::endl; return 0; }
+        if (mwarmup == 0 && !restart) { std::cout << "WARNING: Nothing left to do since mwarmup is zero." << std::endl; return 0; }
         PetscErrorCode ierr;
         t0abs = Now();
+        if (restart) { /* the warm-up is replaced by loading the blocks of the previous run (:736-757) */
+            std::cout << "Loading blocks from file..." << std::endl;
+            if (num_sys_blocks != num_sites - 1) SETERRQ(mpi_comm, 1, "Sweep.dat does not belong to this lattice (num_sys_blocks).");
+            sys_blocks.resize((size_t)num_sys_blocks);
+            for (PetscInt iblock = 0; iblock < sys_ninit; ++iblock) {
+                const std::string path_read = restart_dir + BlockDir("Sys", iblock);
+                std::cout << "  Reading Block " << iblock << " from: " << path_read << std::endl;
+                ierr = BlockIO::Load(sys_blocks[(size_t)iblock], path_read); CHKERRQ(ierr);
+            }
+            PrintLines();
+            warmed_up = PETSC_TRUE;
+            return 0;
+        }
         if (warmed_up) SETERRQ(mpi_comm, 1, "Warmup has already been called, and it can only be called once.");
         printf("WARMUP\n");
         num_sys_blocks = num_sites - 1;
@@ -228,6 +270,7 @@ public:
         }
         if (sys_ninit != num_sites / 2) SETERRQ2(mpi_comm, 1, "Expected sys_ninit = num_sites/2 = %lld. Got %lld.", LLD(num_sites / 2), LLD(sys_ninit));
         warmed_up = PETSC_TRUE;
+        ierr = SaveSweepsData(); CHKERRQ(ierr);
         PrintLines();
         ++LoopIdx;
         return 0;
@@ -235,7 +278,7 @@ public:
 
     /** :864-993 */
     PetscErrorCode Sweeps() {
-        if (dry_run || mwarmup == 0) return 0;
+        if (dry_run || (mwarmup == 0 && !restart)) return 0;
         PetscErrorCode ierr;
         if (sweep_mode == SWEEP_MODE_NSWEEPS) {
             for (msweep_idx = 0; msweep_idx < nsweeps; ++msweep_idx) { ierr = SingleSweep(mwarmup); CHKERRQ(ierr); }
@@ -299,6 +342,7 @@ public:
         sweeps_mstates.push_back(MStates);
         sweeps_seconds.push_back(Now() - tsweep0);
         printf("  Sweep time: %.6f s (%lld steps)\n", sweeps_seconds.back(), LLD(StepIdx));
+        ierr = SaveSweepsData(); CHKERRQ(ierr);
         ++LoopIdx;
         PrintLines();
         return 0;
@@ -398,11 +442,15 @@ private:
         DMRGX_CALL(dmrgx_eigs_smallest(H.h, &eps_opts, &gse_r, gsv_r.d, &eps_stats));
         step_data.GSEnergy = gse_r;
         total_matvecs += eps_stats.nmatvec;
+        double h_bytes = 0, h_flops = 0;
+        { dmrgx_int hn, hnt, t1, t2; dmrgx_hshell_stats(H.h, &hn, &hnt, &h_bytes, &h_flops, &t1, &t2); }
         ierr = MatDestroy_KronSumShell(&H); CHKERRQ(ierr);
         const double tdiag = Tick();
+        total_matvec_flops += h_flops * (double)eps_stats.nmatvec;
         timings_data.tDiag = tdiag - tkron;
-        if (verbose) printf("* Solve Ground State:    %12.6f s   (%lld H*psi, residual %.3g%s)\n", timings_data.tDiag, LLD(eps_stats.nmatvec), eps_stats.resid,
-                            eps_stats.converged ? "" : ", NOT converged");
+        if (verbose) printf("* Solve Ground State:    %12.6f s   (%lld H*psi of %.2f GFLOP, %.1f TFLOP/s incl. orthogonalisation, residual %.3g%s)\n",
+                            timings_data.tDiag, LLD(eps_stats.nmatvec), h_flops * 1e-9, h_flops * (double)eps_stats.nmatvec / timings_data.tDiag * 1e-12,
+                            eps_stats.resid, eps_stats.converged ? "" : ", NOT converged");
         if (no_symm) SETERRQ(mpi_comm, PETSC_ERR_SUP, "Unsupported option: no_symm.");
 
         /* reduced density matrices and the rotation */
@@ -446,6 +494,7 @@ private:
         ierr = SaveTimingsData(timings_data); CHKERRQ(ierr);
         ++GlobIdx;
         ++StepIdx;
+        ++rows_written;
         return 0;
     }
 
@@ -489,6 +538,40 @@ private:
         return 0;
     }
 
+    static std::string BlockDir(const std::string& BlockType, const PetscInt& iblock) { /* :2456-2464: "Sys_000000009/" */
+        std::ostringstream oss; oss << BlockType << "_" << std::setfill('0') << std::setw(9) << iblock << "/"; return oss.str();
+    }
+    static std::string SweepDir(const PetscInt& isweep) { /* :2474-2481: "Sweep_000000002/" */
+        std::ostringstream oss; oss << "Sweep_" << std::setfill('0') << std::setw(9) << isweep << "/"; return oss.str();
+    }
+    /** :2727-2764 — Hamiltonian.dat, PetscOptions.dat, Sweep.dat and (here) the blocks themselves, at the end of a completed loop */
+    PetscErrorCode SaveSweepsData() {
+        if (!do_save_blocks) return 0;
+        PetscErrorCode ierr;
+        const std::string dir = scratch_dir + SweepDir(LoopIdx);
+        ierr = Makedir(dir); CHKERRQ(ierr);
+        for (PetscInt iblock = 0; iblock < sys_ninit; ++iblock) {
+            if (!sys_blocks[(size_t)iblock].Initialized()) continue;
+            ierr = BlockIO::Save(sys_blocks[(size_t)iblock], dir + BlockDir("Sys", iblock), io_int_bytes); CHKERRQ(ierr);
+        }
+        ierr = Ham.SaveAsOptions(dir + "Hamiltonian.dat"); CHKERRQ(ierr);
+        {
+            std::ofstream f((dir + "PetscOptions.dat").c_str());
+            for (const char* key : {"-spin", "-mstates", "-mwarmup", "-nsweeps", "-msweeps", "-maxnsweeps"}) {
+                std::string v; PetscBool set;
+                PetscOptions::DB().GetString(key, v, &set);
+                if (set) f << key << " " << (v.empty() ? "yes" : v) << std::endl;
+            }
+        }
+        std::ofstream f((dir + "Sweep.dat").c_str());
+        const PetscInt num_env_blocks = 1, env_ninit = 0;
+#define SWEEP_DUMP(VAR) f << std::setw(20) << (#VAR) << "  " << (VAR) << "\n";
+        SWEEP_DUMP(GlobIdx); SWEEP_DUMP(LoopIdx); SWEEP_DUMP(num_sys_blocks); SWEEP_DUMP(num_env_blocks); SWEEP_DUMP(sys_ninit); SWEEP_DUMP(env_ninit);
+        SWEEP_DUMP(num_sites); SWEEP_DUMP(sweep_mode); SWEEP_DUMP(msweep_idx);
+#undef SWEEP_DUMP
+        return 0;
+    }
+
     /** :2484-2513 */
     PetscErrorCode SaveStepHeaders() {
         fprintf(fp_step, "{\n  \"headers\" : [");
@@ -502,7 +585,7 @@ private:
     }
     /** :2516-2566 (tabular form, the reference's default) */
     PetscErrorCode SaveStepData(const StepData& d) {
-        fprintf(fp_step, "%s", GlobIdx ? ",\n" : "");
+        fprintf(fp_step, "%s", rows_written ? ",\n" : ""); /* (the reference keys the comma on GlobIdx, which breaks the file after a restart) */
         fprintf(fp_step, "    [ %lld, %s, %lld, %lld, ", LLD(GlobIdx), LoopType ? "\"Sweep\"" : "\"Warmup\"", LLD(LoopIdx), LLD(StepIdx));
         fprintf(fp_step, "%lld, %lld, %lld, %lld, ", LLD(d.NumSites_Sys), LLD(d.NumSites_Env), LLD(d.NumSites_SysEnl), LLD(d.NumSites_EnvEnl));
         fprintf(fp_step, "%lld, %lld, %lld, %lld, ", LLD(d.NumStates_Sys), LLD(d.NumStates_Env), LLD(d.NumStates_SysEnl), LLD(d.NumStates_EnvEnl));
@@ -518,7 +601,7 @@ private:
         return 0;
     }
     PetscErrorCode SaveTimingsData(const TimingsData& d) {
-        fprintf(fp_timings, "%s", GlobIdx ? ",\n" : "");
+        fprintf(fp_timings, "%s", rows_written ? ",\n" : "");
         fprintf(fp_timings, "    [ %lld, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g ]", LLD(GlobIdx), d.Total, d.tEnlr, d.tKron, d.tDiag, d.tRdms, d.tRotb);
         fflush(fp_timings);
         return 0;
@@ -526,7 +609,7 @@ private:
     /** :2618-2665 — the unsorted, per-block-grouped spectra (what GetTruncation hands over at :1790-1793) */
     PetscErrorCode SaveEntanglementSpectra(const BasisTransformation& L, const std::vector<PetscReal>& qn_L, const BasisTransformation& R,
                                            const std::vector<PetscReal>& qn_R) {
-        fprintf(fp_entanglement, "%s", GlobIdx ? ",\n" : "");
+        fprintf(fp_entanglement, "%s", rows_written ? ",\n" : "");
         fprintf(fp_entanglement, "  {\n    \"GlobIdx\": %lld,\n", LLD(GlobIdx));
         const BasisTransformation* bt[2] = {&L, &R};
         const std::vector<PetscReal>* qn[2] = {&qn_L, &qn_R};
@@ -557,7 +640,7 @@ private:
         for (size_t i = 0; i < sweeps_mstates.size(); ++i) fprintf(fp_data, "%s %lld", i ? "," : "", LLD(sweeps_mstates[i]));
         fprintf(fp_data, " ],\n    \"Seconds\": [");
         for (size_t i = 0; i < sweeps_seconds.size(); ++i) fprintf(fp_data, "%s %.9g", i ? "," : "", sweeps_seconds[i]);
-        fprintf(fp_data, " ]\n  },\n  \"NumMatVecs\": %lld", LLD(total_matvecs));
+        fprintf(fp_data, " ]\n  },\n  \"NumMatVecs\": %lld,\n  \"MatVecFlops\": %.6g", LLD(total_matvecs), total_matvec_flops);
         fflush(fp_data);
         return 0;
     }
@@ -576,7 +659,10 @@ private:
     Hamiltonian Ham;
     Block SingleSite;
     Block& AddSite = SingleSite;
-    std::string scratch_dir = ".";
+    std::string scratch_dir = ".", restart_dir;
+    PetscBool restart = PETSC_FALSE, do_save_blocks = PETSC_FALSE;
+    int io_int_bytes = 4;
+    static const PetscInt MAX_SWEEP_IDX = 10000;
     FILE *fp_step = NULL, *fp_timings = NULL, *fp_entanglement = NULL, *fp_data = NULL, *fp_corr = NULL;
     PetscInt GlobIdx = 0;
     Step_t LoopType = NullStep;
@@ -587,5 +673,6 @@ private:
     std::vector<PetscReal> trunc_err;
     double t0abs = 0.0;
     dmrgx_eigs_opts eps_opts = {1e-8, 16, 0, 20261018ULL}; /* SLEPc defaults: tol 1e-8, ncv 16 */
-    long long total_matvecs = 0;
+    long long total_matvecs = 0, rows_written = 0;
+    double total_matvec_flops = 0;
 };

@@ -51,3 +51,88 @@ def test_sweep_modes_and_errors(exe, tmp_path):
     assert r.returncode != 0 and "same number of items" in r.stderr
     r = subprocess.run([exe, "-Lx", "3", "-Ly", "1", "-mwarmup", "8", "-data_dir", str(tmp_path) + "/e/"], capture_output=True, text=True)
     assert r.returncode != 0 and "must be even" in r.stderr
+
+
+def read_petsc_mat(path, int_bytes=4):
+    """PETSc binary AIJ matrix (MatView on a binary viewer): big-endian classid 1211216, M, N, nz, row lengths, columns, values."""
+    import numpy as np
+    raw = open(path, "rb").read()
+    it = np.dtype(">i4" if int_bytes == 4 else ">i8")
+    hdr = np.frombuffer(raw, it, 4)
+    assert hdr[0] == 1211216
+    M, N, nz = int(hdr[1]), int(hdr[2]), int(hdr[3])
+    off = 4 * int_bytes
+    rowlen = np.frombuffer(raw, it, M, off); off += M * int_bytes
+    col = np.frombuffer(raw, it, nz, off); off += nz * int_bytes
+    val = np.frombuffer(raw, ">f8", nz, off); off += nz * 8
+    assert off == len(raw)
+    A = np.zeros((M, N))
+    r = np.repeat(np.arange(M), rowlen)
+    A[r, col] = val
+    return A
+
+
+def test_checkpoint_format_and_restart(exe, orc, tmp_path):
+    """-scratch_dir writes the reference's on-disk block format (BlockInfo.dat, QuantumNumbers.dat, PETSc binary .mat) after
+    every loop; -restart_dir continues from it and reproduces the uninterrupted run."""
+    import json
+    import numpy as np
+    ham = ["-Lx", "12", "-Ly", "1", "-heisenberg", "1", "-BCopen", "-H_eps_tol", "1e-12", "-do_correlators", "0"]
+    s1 = str(tmp_path) + "/scratch1/"
+    r = subprocess.run([exe] + ham + ["-mwarmup", "16", "-msweeps", "24", "-scratch_dir", s1, "-data_dir", str(tmp_path) + "/d1/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    sweep_dir = s1 + "Sweep_000000001/"
+    info = dict(l.split() for l in open(sweep_dir + "Sys_000000005/BlockInfo.dat"))
+    assert info["NumBytesPetscInt"] == "4" and info["NumBytesPetscScalar"] == "8" and info["PetscUseComplex"] == "0"
+    assert info["SpinTypeKey"] == "102" and info["NumSites"] == "6"
+    qn = [l.split() for l in open(sweep_dir + "Sys_000000005/QuantumNumbers.dat")]
+    assert sum(int(a) for a, _ in qn) == int(info["NumStates"]) and len(qn) == int(info["NumSectors"])
+    # the saved matrices against the oracle's block
+    d = orc.DMRG(Lx=12, Ly=1, heisenberg=1.0, bcx=0, bcy=0, eps_tol=1e-12)
+    d.warmup(16); d.sweep(24)
+    Ho = d.block(5).get_op_dense(orc.OP_H)
+    Hd = read_petsc_mat(sweep_dir + "Sys_000000005/H_000000000.mat")
+    # (the kept multiplets at a degenerate cut may differ between the two codes, the low end of the block spectrum may not)
+    assert Hd.shape == Ho.shape and abs(np.linalg.eigvalsh(Hd)[0] - np.linalg.eigvalsh(Ho)[0]) < 1e-9 and np.abs(Hd - Hd.T).max() < 1e-12
+    Sz = read_petsc_mat(sweep_dir + "Sys_000000005/Sz_000000003.mat")
+    assert np.abs(Sz - Sz.T).max() < 1e-12 and abs(np.abs(np.linalg.eigvalsh(Sz)).max() - 0.5) < 1e-9
+    keys = dict(l.split() for l in open(sweep_dir + "Sweep.dat"))
+    assert keys["LoopIdx"] == "1" and keys["num_sys_blocks"] == "11" and keys["sys_ninit"] == "6" and keys["GlobIdx"] == "12"
+    # restart from the checkpoint, one more sweep at m = 32 == the uninterrupted 24,32 run
+    r2 = subprocess.run([exe, "-restart_dir", s1, "-msweeps", "32", "-H_eps_tol", "1e-12", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d2/"],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stdout[-1500:] + r2.stderr[-1500:]
+    assert "Loading blocks from file" in r2.stdout
+    r3 = subprocess.run([exe] + ham + ["-mwarmup", "16", "-msweeps", "24,32", "-data_dir", str(tmp_path) + "/d3/"], capture_output=True, text=True)
+    assert r3.returncode == 0
+    t2 = json.load(open(str(tmp_path) + "/d2/DMRGSteps.json"))["table"]
+    t3 = json.load(open(str(tmp_path) + "/d3/DMRGSteps.json"))["table"]
+    assert len(t2) == 8 and t2[0][0] == 12 and t2[0][2] == 2                      # GlobIdx / LoopIdx continue
+    for a, b in zip(t2, t3[-8:]):
+        assert a[:15] == b[:15] and abs(a[-1] - b[-1]) <= 1e-10 * abs(b[-1])
+    assert abs(t2[-1][-1] - (-5.142090632841)) < 1e-9
+
+
+def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path):
+    """BASELINE configs[4]: blocks saved by the driver are read back through Block.InitializeFromDisk and the sweep-midpoint
+    superblock built from them has the energy the driver reported for that step."""
+    import json
+    import dmrgx_loader
+    import bench_workload as W
+    args = ["-Lx", "4", "-Ly", "4", "-J1", "0.5", "-Jz1", "1", "-J2", "0.25", "-Jz2", "0.5", "-mwarmup", "24", "-msweeps", "32", "-H_eps_tol", "1e-12",
+            "-do_correlators", "0", "-scratch_dir", str(tmp_path) + "/s/", "-data_dir", str(tmp_path) + "/d/"]
+    r = subprocess.run([exe] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    P = dmrgx_loader.load_package()
+    P.use_library(os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
+    try:
+        ctx = P.Context(0)
+        W.CONFIGS["j1j2_4x4"] = dict(Lx=4, Ly=4, J1=0.5, Jz1=1.0, J2=0.25, Jz2=0.5, bcx=0, bcy=1)
+        wl = W.DiskWorkload(P, ctx, "j1j2_4x4", str(tmp_path) + "/s/Sweep_000000001/")
+        e, psi, st = wl.shell.EPSSolve(tol=1e-12)
+        last = json.load(open(str(tmp_path) + "/d/DMRGSteps.json"))["table"][-1]
+        assert wl.m == last[8] and wl.n == last[14]
+        assert abs(e - last[-1]) <= 1e-10 * abs(e)
+        ctx.close()
+    finally:
+        P.use_library(None)
