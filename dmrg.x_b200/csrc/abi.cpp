@@ -181,6 +181,14 @@ dmrgx_int dmrgx_hshell_plan_items(dmrgx_hshell h, int stage, dmrgx_int cap, dmrg
     }
     return n;
 }
+/* plan introspection: how often each segment type (dev::SegType 0..5) is executed by the items of a stage */
+int dmrgx_hshell_plan_segtypes(dmrgx_hshell h, int stage, dmrgx_int* out6) {
+    const Plan& p = stage == 1 ? H(h)->stage1 : H(h)->stage2;
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    for (const dev::WorkItem& it : p.items)
+        for (int sgi = it.seg_begin; sgi < it.seg_end; ++sgi) out6[p.segs[sgi].type]++;
+    return 0;
+}
 int dmrgx_hshell_stage_exec_flops(dmrgx_hshell h, double* flops1, double* flops2) {
     *flops1 = H(h)->stage1.exec_flops; *flops2 = H(h)->stage2.exec_flops;
     return 0;

@@ -378,40 +378,81 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] += coef * v[mi][ni][0]; acc[mi][ni][1] += coef * v[mi][ni][1]; }
-        } else {
-            /* slow-path segments: each thread updates the accumulator elements it owns */
+        } else if (sg.type == SEG_CSRA) {
+            /* sparse left factor: acc(m,n) += coef * Σ_e val[e] · X(col[e], n).  One walk over the CSR row per accumulator ROW:
+               the index and value of an entry are loaded once and feed the eight columns this thread owns (the four lanes of a
+               quad read 64 contiguous bytes of the dense row), instead of one dependent walk per element */
+            const double* xb = sg.A + (long long)(it.n0 + cbase + 2 * t) * sg.ldb_n;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = rbase + mi * 8 + g;
+                if (mi >= nmi || row >= tm) continue;
+                const int r = sg.row0 + it.m0 + row;
+                const int e1 = sg.rowptr[r + 1];
+                for (int e = sg.rowptr[r]; e < e1; ++e) {
+                    const double v = sg.B[e] * sg.coef;
+                    const double* xr = xb + (long long)sg.colidx[e] * sg.ldb_k;
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int col = cbase + ni * 8 + 2 * t;
+                        if (ni < nni && col < tn) acc[mi][ni][0] += v * xr[(long long)(ni * 8) * sg.ldb_n];
+                        if (ni < nni && col + 1 < tn) acc[mi][ni][1] += v * xr[(long long)(ni * 8 + 1) * sg.ldb_n];
+                    }
+                }
+            }
+        } else if (sg.type == SEG_CSRB) {
+            /* sparse right factor: acc(m,n) += coef * Σ_e val_n[e] · V(m, col_n[e]): one walk per accumulator COLUMN feeding the
+               four rows this thread owns (lock-step walks of the eight columns were measured: no gain, the segment is bound by L2
+               gather traffic, not by the length of the dependent chains) */
+            const double* vb = sg.A + (long long)(it.m0 + rbase + g) * sg.lda_m;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = cbase + ni * 8 + 2 * t + h;
+                    if (ni >= nni || col >= tn) continue;
+                    const int r = sg.row0 + it.n0 + col;
+                    const int e1 = sg.rowptr[r + 1];
+                    for (int e = sg.rowptr[r]; e < e1; ++e) {
+                        const double v = sg.B[e] * sg.coef;
+                        const double* vc = vb + (long long)sg.colidx[e] * sg.lda_k;
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if (mi < nmi && rbase + mi * 8 + g < tm) acc[mi][ni][h] += v * vc[(long long)(mi * 8) * sg.lda_m];
+                    }
+                }
+            }
+        } else if (sg.type == SEG_CSRADD) {
+            /* acc(m,n) += coef * Σ_e val[e] · [col[e] == n + d]: one walk per row, each entry lands in at most one owned column */
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = rbase + mi * 8 + g;
+                if (mi >= nmi || row >= tm) continue;
+                const int r = sg.row0 + it.m0 + row;
+                const int e1 = sg.rowptr[r + 1];
+                for (int e = sg.rowptr[r]; e < e1; ++e) {
+                    const int lc = sg.colidx[e] - sg.d - it.n0 - cbase - 2 * t; /* column relative to this thread's first one */
+                    const double v = sg.B[e] * sg.coef;
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int col = cbase + ni * 8 + 2 * t;
+                        if (ni < nni && lc == ni * 8 && col < tn) acc[mi][ni][0] += v;
+                        if (ni < nni && lc == ni * 8 + 1 && col + 1 < tn) acc[mi][ni][1] += v;
+                    }
+                }
+            }
+        } else if (sg.type == SEG_DIAG) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const int row = rbase + mi * 8 + g;
                 if (mi >= nmi || row >= tm) continue;
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
+                for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int col = cbase + ni * 8 + 2 * t + h;
-                        if (ni >= nni || col >= tn) continue;
-                        const long long gm = it.m0 + row, gn = it.n0 + col;
-                        double v = 0.0;
-                        if (sg.type == SEG_AXPY) {
-                            v = sg.A[gm * sg.lda_m + gn * sg.lda_k];
-                        } else if (sg.type == SEG_DIAG) {
-                            v = (gm + sg.d == gn) ? 1.0 : 0.0;
-                        } else if (sg.type == SEG_CSRA) {
-                            const int r = sg.row0 + (int)gm;
-                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
-                                v += sg.B[e] * sg.A[(long long)sg.colidx[e] * sg.ldb_k + gn * sg.ldb_n];
-                        } else if (sg.type == SEG_CSRB) {
-                            const int r = sg.row0 + (int)gn;
-                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
-                                v += sg.B[e] * sg.A[gm * sg.lda_m + (long long)sg.colidx[e] * sg.lda_k];
-                        } else if (sg.type == SEG_CSRADD) {
-                            const int r = sg.row0 + (int)gm;
-                            for (int e = sg.rowptr[r]; e < sg.rowptr[r + 1]; ++e)
-                                if (sg.colidx[e] == (int)gn + sg.d) v += sg.B[e];
-                        }
-                        acc[mi][ni][h] += sg.coef * v;
+                        if (ni < nni && col < tn && it.m0 + row + sg.d == it.n0 + col) acc[mi][ni][h] += sg.coef;
                     }
-                }
             }
         }
     }

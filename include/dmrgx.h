@@ -116,6 +116,8 @@ int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, doubl
 int dmrgx_hshell_stage_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
 /* the FP64 tensor flops the two launches execute for them (tiles padded to whole DMMA fragments and K chunks) */
 int dmrgx_hshell_stage_exec_flops(dmrgx_hshell h, double* flops_stage1, double* flops_stage2);
+/* plan introspection: executions per segment type {GEMM, AXPY, DIAG, CSRA, CSRB, CSRADD} over the items of a stage */
+int dmrgx_hshell_plan_segtypes(dmrgx_hshell h, int stage, dmrgx_int* out6);
 /* plan introspection: per work item {tm, tn, segments, sum of K of its GEMM segments}; returns the item count */
 dmrgx_int dmrgx_hshell_plan_items(dmrgx_hshell h, int stage, dmrgx_int cap, dmrgx_int* out4);
 /* same with HOST buffers (the Vec arrays of the PETSc callback): H2D, (all-gather,) apply, D2H, synchronous.  x and y are
