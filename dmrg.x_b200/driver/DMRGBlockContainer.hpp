@@ -548,11 +548,13 @@ private:
     PetscErrorCode SaveSweepsData() {
         if (!do_save_blocks) return 0;
         PetscErrorCode ierr;
+        int spin_type_key = 102; /* SpinOneHalf = 102, SpinOne = 101 (include/DMRGBlock.hpp:51-55) */
+        { std::string sp; PetscBool set; PetscOptions::DB().GetString("-spin", sp, &set); if (set && sp == "1") spin_type_key = 101; }
         const std::string dir = scratch_dir + SweepDir(LoopIdx);
         ierr = Makedir(dir); CHKERRQ(ierr);
         for (PetscInt iblock = 0; iblock < sys_ninit; ++iblock) {
             if (!sys_blocks[(size_t)iblock].Initialized()) continue;
-            ierr = BlockIO::Save(sys_blocks[(size_t)iblock], dir + BlockDir("Sys", iblock), io_int_bytes); CHKERRQ(ierr);
+            ierr = BlockIO::Save(sys_blocks[(size_t)iblock], dir + BlockDir("Sys", iblock), io_int_bytes, spin_type_key); CHKERRQ(ierr);
         }
         ierr = Ham.SaveAsOptions(dir + "Hamiltonian.dat"); CHKERRQ(ierr);
         {

@@ -136,3 +136,11 @@ def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path):
         ctx.close()
     finally:
         P.use_library(None)
+
+
+def test_spin_one_chain_matches_oracle(exe, orc, tmp_path):
+    """-spin 1 (src/DMRGBlock.cpp:54-94, 1151-1156, 1210-1215): three-state sites, sector steps of one."""
+    docs, out = dc.run_driver(exe, tmp_path, ["-Lx", 8, "-Ly", 1, "-heisenberg", 1, "-BCopen", "-spin", 1, "-do_correlators", 0], 27, [40])
+    ref, _ = dc.compare_with_oracle(orc, docs, dict(Lx=8, Ly=1, heisenberg=1.0, bcx=0, bcy=0, spin_twice=2), 27, [40])
+    # kept-state counts inside degenerate SU(2) multiplets may differ after the first tie; the converged energy may not
+    assert abs(docs["DMRGSteps"]["table"][-1][-1] - ref[-1]["GSEnergy"]) <= 1e-9 * abs(ref[-1]["GSEnergy"])
