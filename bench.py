@@ -181,12 +181,8 @@ def main():
         rows = int(max(probe, min(n, budget / per_row)))
         r0 = max(0, mid - rows // 2); r1 = min(n, r0 + rows)
         sh = O.Shell(kb, wl.terms, rows=(r0, r1))
-        # algorithmic bytes of the same workload (same definition as our arm): 16·D + distinct operator panels
-        tile_bytes = 0
-        for key, (rp, ci, vv) in wl.host["ops"].items():
-            if len(vv):
-                tile_bytes += 8 * len(vv)
-        alg_bytes = 16.0 * n + tile_bytes
+        # algorithmic bytes of the same workload, same definition as our arm, computed without the library
+        alg_bytes = float(W.algorithmic_bytes(wl.host, wl.terms, N // 2 - 1, n))
         for _ in range(args.warmup):
             sh.apply(x, cores)
         t = time.time()

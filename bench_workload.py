@@ -100,6 +100,27 @@ def synth_block_host(m, nsites, used, seed=SEED, sigma=2.5):
     return dict(nsites=nsites, qn=qn, sizes=sz, ops=ops)
 
 
+def algorithmic_bytes(host, terms_super, nsites_blk, D):
+    """SURVEY.md §8d, without touching the library: 16*D (psi in, y out) + every distinct ORIGINAL operator panel once —
+    Sz_i / Sp_i of the block sites that appear in L-R terms (the added site's operators are scaled identities, 0 bytes; the
+    environment is the mirrored system block, so both sides share the panels) + the enlarged block's H, dense per sector."""
+    nenl = nsites_blk + 1
+    sites = set()
+    for (a, _, i, _, j) in terms_super:
+        if a != 0 and i < nenl <= j < 2 * nenl:
+            sites.add(i); sites.add(2 * nenl - 1 - j)
+    tb = 0
+    for i in sites:
+        if i < nsites_blk:
+            tb += 8 * len(host["ops"][("Sz", i)][2]) + 8 * len(host["ops"][("Sp", i)][2])
+    enl = {}
+    for q, n in zip(host["qn"], host["sizes"]):
+        for dq in (+0.5, -0.5):
+            enl[q + dq] = enl.get(q + dq, 0) + int(n)
+    tb += 8 * sum(v * v for v in enl.values())
+    return 16 * D + tb
+
+
 class Workload:
     """Everything one H·psi benchmark / parity case needs, on the product side."""
 
