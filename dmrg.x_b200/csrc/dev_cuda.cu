@@ -879,11 +879,119 @@ void bcast_batch(Stream* st, int n, double* const* d_ptr, const long long* count
     NCCL_OK(nccl().GroupEnd());
 }
 
+/* ================================================================================================
+ *  Small reduced-density-matrix blocks (n <= 64): batched cyclic Jacobi, one CTA per block, the block and its
+ *  eigenvector matrix in shared memory.  A round of the round-robin schedule holds n/2 disjoint index pairs; their
+ *  rotations are computed from the current matrix and applied together (columns, then rows), so a sweep is n-1 rounds
+ *  of fully parallel updates.  Jacobi is accurate to working precision in the small eigenvalues too, which is what the
+ *  truncation ranks.  Larger blocks go to cuSOLVER's syevd on the solver lanes.
+ *  Replaces EigRDM_BlockDiag / EPSLAPACK (include/DMRGBlockContainer.hpp:1962-2003) for these sizes.
+ * ============================================================================================== */
+constexpr int JAC_NMAX = 64, JAC_LD = JAC_NMAX + 1, JAC_THREADS = 256;
+struct JacobiJob { double* A; double* w; int n; int pad; };
+
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const JacobiJob* __restrict__ jobs) {
+    extern __shared__ double jsm[];
+    double* A = jsm;                       /* [JAC_NMAX][JAC_LD] */
+    double* V = jsm + JAC_NMAX * JAC_LD;   /* eigenvectors in columns */
+    __shared__ double cs[JAC_NMAX / 2][2];
+    __shared__ int pq[JAC_NMAX / 2][2];
+    __shared__ double red[JAC_THREADS / 32][2];
+    __shared__ double offdiag[2];
+    const JacobiJob job = jobs[blockIdx.x];
+    const int n = job.n, tid = threadIdx.x;
+    const int ne = (n + 1) & ~1; /* the schedule needs an even count: an odd block gets an idle dummy index */
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int i = e / n, j = e % n;
+        A[i * JAC_LD + j] = job.A[e];
+        V[i * JAC_LD + j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        /* convergence: off-diagonal weight against the diagonal's */
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < n * n; e += JAC_THREADS) {
+            const int i = e / n, j = e % n;
+            const double a = A[i * JAC_LD + j];
+            if (i == j) dg += a * a; else off += a * a;
+        }
+        off = warp_sum(off); dg = warp_sum(dg);
+        if ((tid & 31) == 0) { red[tid >> 5][0] = off; red[tid >> 5][1] = dg; }
+        __syncthreads();
+        if (tid == 0) {
+            double o = 0, d = 0;
+            for (int k = 0; k < JAC_THREADS / 32; ++k) { o += red[k][0]; d += red[k][1]; }
+            offdiag[0] = o; offdiag[1] = d;
+        }
+        __syncthreads();
+        if (offdiag[0] == 0.0 || offdiag[0] <= 1e-33 * (offdiag[0] + offdiag[1])) break;
+        for (int round = 0; round < ne - 1; ++round) {
+            /* round-robin pairing: index ne-1 stays, the others rotate */
+            if (tid < ne / 2) {
+                int a = tid == 0 ? ne - 1 : (round + tid) % (ne - 1);
+                int b = (round + ne - 1 - tid) % (ne - 1);
+                int p = a < b ? a : b, q = a < b ? b : a;
+                double c = 1.0, sn = 0.0;
+                if (q < n) {
+                    const double apq = A[p * JAC_LD + q];
+                    if (apq != 0.0) {
+                        const double theta = (A[q * JAC_LD + q] - A[p * JAC_LD + p]) / (2.0 * apq);
+                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        sn = tt * c;
+                    }
+                } else { p = -1; }
+                pq[tid][0] = p; pq[tid][1] = q;
+                cs[tid][0] = c; cs[tid][1] = sn;
+            }
+            __syncthreads();
+            /* columns p,q of A and of V */
+            for (int e = tid; e < (ne / 2) * n; e += JAC_THREADS) {
+                const int k = e / n, i = e % n;
+                const int p = pq[k][0], q = pq[k][1];
+                if (p < 0) continue;
+                const double c = cs[k][0], sn = cs[k][1];
+                const double x = A[i * JAC_LD + p], y = A[i * JAC_LD + q];
+                A[i * JAC_LD + p] = c * x - sn * y; A[i * JAC_LD + q] = sn * x + c * y;
+                const double vx = V[i * JAC_LD + p], vy = V[i * JAC_LD + q];
+                V[i * JAC_LD + p] = c * vx - sn * vy; V[i * JAC_LD + q] = sn * vx + c * vy;
+            }
+            __syncthreads();
+            /* rows p,q of A */
+            for (int e = tid; e < (ne / 2) * n; e += JAC_THREADS) {
+                const int k = e / n, j = e % n;
+                const int p = pq[k][0], q = pq[k][1];
+                if (p < 0) continue;
+                const double c = cs[k][0], sn = cs[k][1];
+                const double x = A[p * JAC_LD + j], y = A[q * JAC_LD + j];
+                A[p * JAC_LD + j] = c * x - sn * y; A[q * JAC_LD + j] = sn * x + c * y;
+            }
+            __syncthreads();
+        }
+    }
+    /* ascending order by rank (stable on ties); row k of the output = k-th eigenvector */
+    __shared__ int rank_of[JAC_NMAX];
+    if (tid < n) {
+        const double di = A[tid * JAC_LD + tid];
+        int r = 0;
+        for (int j = 0; j < n; ++j) { const double dj = A[j * JAC_LD + j]; r += (dj < di || (dj == di && j < tid)) ? 1 : 0; }
+        rank_of[tid] = r;
+        job.w[r] = di;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int col = e / n, i = e % n; /* eigenvector `col` of V, component i */
+        job.A[(long long)rank_of[col] * n + i] = V[i * JAC_LD + col];
+    }
+}
+
 /* One worker thread per lane pulls blocks (largest first) from a shared counter: cuSOLVER's syevd synchronises with the
    host internally, so concurrency across blocks needs concurrent host callers as well as separate streams. */
 int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, double* const* d_w) {
     if (nblocks <= 0) return 0;
-    if (st->lanes.empty()) {
+    bool any_large = false;
+    for (int b = 0; b < nblocks; ++b) any_large = any_large || n[b] > JAC_NMAX;
+    if (any_large && st->lanes.empty()) {
         st->lanes.resize(SOLVER_LANES);
         st->ev_lane.resize(SOLVER_LANES);
         CUDA_OK(cudaEventCreateWithFlags(&st->ev_main, cudaEventDisableTiming));
@@ -896,8 +1004,24 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
             CUDA_OK(cudaEventCreateWithFlags(&st->ev_lane[i], cudaEventDisableTiming));
         }
     }
+    /* blocks of up to 64 states: one launch of the batched Jacobi kernel on the main stream */
+    {
+        std::vector<JacobiJob> jobs;
+        for (int b = 0; b < nblocks; ++b) if (n[b] > 0 && n[b] <= JAC_NMAX) jobs.push_back({d_A[b], d_w[b], n[b], 0});
+        if (!jobs.empty()) {
+            constexpr int smem = 2 * JAC_NMAX * JAC_LD * (int)sizeof(double);
+            static bool configured = false;
+            if (!configured) { CUDA_OK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+            JacobiJob* d_jobs = (JacobiJob*)malloc_bytes(st, jobs.size() * sizeof(JacobiJob));
+            CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(JacobiJob), cudaMemcpyHostToDevice, st->s));
+            jacobi_eig_kernel<<<(int)jobs.size(), JAC_THREADS, smem, st->s>>>(d_jobs);
+            LAUNCH_CHECK();
+            CUDA_OK(cudaStreamSynchronize(st->s)); /* the host job list must outlive the copy */
+            free_bytes(st, d_jobs);
+        }
+    }
     std::vector<int> order;
-    for (int b = 0; b < nblocks; ++b) if (n[b] > 0) order.push_back(b);
+    for (int b = 0; b < nblocks; ++b) if (n[b] > JAC_NMAX) order.push_back(b);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
     const int nl = (int)std::min<size_t>(st->lanes.size(), order.size());
     if (nl == 0) return 0;
