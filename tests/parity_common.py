@@ -153,3 +153,57 @@ def run_step_parity(P, O, ctx, ham, nsys, nenv, m_prep, m_keep, rng, tol=1e-12):
         assert np.abs(dense_op(pnew, P.OpSz, i) - Up @ Sz_enl @ Up.T).max() < 1e-11
     assert pnew.CheckOperatorBlocks() == 0
     return e, e_ref
+
+
+def check_correlator_products(P, orc, ctx, ham):
+    """dmrgx_hshell_create_product (CalculateOperatorProducts + KronConstruct, include/DMRGBlockContainer.hpp:2262-2296,
+    2340-2425): <psi| (O_1 O_2 ...)_sys ⊗ (O'_1 ...)_env |psi> against dense numpy products of the oracle's operators."""
+    import ctypes as C
+    SM = -1  # Op_t OpSm (include/DMRGBlock.hpp:21-27)
+    ham = J1J2_CYL
+    d = orc.DMRG(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"])
+    d.warmup(20)
+    oL = orc.kron_eye(d.block(6), orc.Block.single_site(), lr_terms(orc, ham, 8))
+    okb = orc.KronBlocks(oL, oL, [0.0])
+    pL = upload_block(P, ctx, oL, orc)
+    pkb = P.KronBlocks(pL, pL, [0.0])
+    rng = np.random.default_rng(5)
+    psi = rng.standard_normal(okb.num_states()); psi /= np.linalg.norm(psi)
+    dpsi = ctx.vec(len(psi), psi)
+    qn, il, ir, sz, off = okb.data()
+    oqn, osz = oL.sectors()
+    ooff = np.concatenate([[0], np.cumsum(osz)])
+    dense = {(op, i): oL.get_op_dense(op, i) for op in (orc.OP_SZ, orc.OP_SP) for i in range(8)}
+    for i in range(8):
+        dense[(SM, i)] = dense[(orc.OP_SP, i)].T
+
+    def expect_dense(lops, rops):
+        n = oL.nstates
+        A = np.eye(n); B = np.eye(n)
+        for o in lops:
+            A = A @ dense[o]
+        for o in rops:
+            B = B @ dense[o]
+        # psi as a block matrix over sector pairs: Psi[l, r] with l, r global block indices
+        Psi = np.zeros((n, n))
+        for p in range(len(qn)):
+            nl, nr = osz[il[p]], osz[ir[p]]
+            Psi[ooff[il[p]]:ooff[il[p]] + nl, ooff[ir[p]]:ooff[ir[p]] + nr] = psi[off[p]:off[p + 1]].reshape(nl, nr)
+        return float(np.sum(Psi * (A @ Psi @ B.T)))
+
+    L = P.lib()
+    cases = [([(orc.OP_SZ, 3)], []), ([(orc.OP_SZ, 2), (orc.OP_SZ, 5)], []), ([(orc.OP_SP, 1), (SM, 6)], []),
+             ([(orc.OP_SZ, 7)], [(orc.OP_SZ, 7)]), ([(orc.OP_SP, 4)], [(SM, 0), (orc.OP_SZ, 3)]),
+             ([(orc.OP_SZ, 0), (orc.OP_SZ, 1), (orc.OP_SZ, 2)], [(orc.OP_SZ, 6), (orc.OP_SZ, 5)]), ([], [(orc.OP_SZ, 2)])]
+    for lops, rops in cases:
+        h = C.c_void_p()
+        la = np.array([o for o, _ in lops], np.int32); ls = np.array([s for _, s in lops], np.int64)
+        ra = np.array([o for o, _ in rops], np.int32); rs = np.array([s for _, s in rops], np.int64)
+        e = L.dmrgx_hshell_create_product(pkb.h, C.c_longlong(len(lops)), la.ctypes.data_as(C.c_void_p), ls.ctypes.data_as(C.c_void_p),
+                                          C.c_longlong(len(rops)), ra.ctypes.data_as(C.c_void_p), rs.ctypes.data_as(C.c_void_p), C.byref(h))
+        assert e == 0, L.dmrgx_last_error()
+        v = C.c_double()
+        assert L.dmrgx_expect(h, dpsi.ptr, C.byref(v)) == 0
+        L.dmrgx_hshell_destroy(h)
+        ref = expect_dense(lops, rops)
+        assert abs(v.value - ref) < 1e-12, (lops, rops, v.value, ref)

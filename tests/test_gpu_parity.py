@@ -165,3 +165,7 @@ def test_exact_chain_sparse_workload_ground_state(P, ctx):
     x = sw.random_state(4); y = sw.random_state(5)
     Hx = sw.shell.MatMult_host(x); Hy = sw.shell.MatMult_host(y)
     assert abs(y @ Hx - x @ Hy) < 1e-12
+
+
+def test_correlator_operator_products_match_dense(P, ctx, orc):
+    pc.check_correlator_products(P, orc, ctx, J1J2_CYL)

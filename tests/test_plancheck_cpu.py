@@ -153,3 +153,7 @@ def test_exact_chain_sparse_workload_ground_state(P, ctx):
     assert sw.n == 924
     e, psi, st = sw.shell.EPSSolve(tol=1e-12)
     assert st["converged"] and abs(e - (-5.142090632841)) < 1e-9
+
+
+def test_correlator_operator_products_match_dense(P, ctx, orc):
+    pc.check_correlator_products(P, orc, ctx, J1J2_CYL)
