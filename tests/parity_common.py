@@ -160,7 +160,7 @@ def check_correlator_products(P, orc, ctx, ham):
     2340-2425): <psi| (O_1 O_2 ...)_sys ⊗ (O'_1 ...)_env |psi> against dense numpy products of the oracle's operators."""
     import ctypes as C
     SM = -1  # Op_t OpSm (include/DMRGBlock.hpp:21-27)
-    ham = J1J2_CYL
+
     d = orc.DMRG(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"])
     d.warmup(20)
     oL = orc.kron_eye(d.block(6), orc.Block.single_site(), lr_terms(orc, ham, 8))
