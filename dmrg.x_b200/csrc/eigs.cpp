@@ -8,6 +8,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -82,11 +83,35 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     dev::allreduce_sum(st, d_nrm2, 1);
     dev::scale_inv_norm(st, V, d_nrm2, V, N);
 
+    const char* early_env = getenv("DMRGX_EARLY_TEST_MIN"); /* test hook: the size above which the in-cycle stopping test is on */
+    const bool early_test = NG >= (early_env ? atoll(early_env) : 50000LL);
     int nc = ld, k = 0;
     double theta = 0, resid = 0;
     for (long long it = 0; it < max_it; ++it) {
         double beta_last = 0;
         bool invariant = false;
+        nc = ld;
+        int absorbed = k; /* rows [k, absorbed) of the coefficient table are already in T */
+        /* bring the coefficient rows [absorbed, upto) to the host and enter them into the projected matrix; true when an
+           invariant subspace was reached (the steps queued after it worked on a null direction and are ignored) */
+        auto absorb_rows = [&](int upto) -> bool {
+            if (upto <= absorbed) return false;
+            dev::d2h(st, hh.data() + (size_t)absorbed * RW, d_tab + (size_t)absorbed * RW, (size_t)(upto - absorbed) * RW * 8);
+            dev::sync(st);
+            for (int j = absorbed; j < upto; ++j) {
+                const double* r = hh.data() + (size_t)j * RW;
+                for (int i = 0; i <= j; ++i) {
+                    const double c = r[i] + r[(ld + 1) + i];
+                    T[(size_t)i * ld + j] = c;
+                    T[(size_t)j * ld + i] = c;
+                }
+                const double b = std::sqrt(std::max(0.0, r[2 * (ld + 1)]));
+                beta_last = b;
+                if (!(b >= 1e-14)) { nc = j + 1; invariant = true; absorbed = upto; return true; }
+            }
+            absorbed = upto;
+            return false;
+        };
         for (int j = k; j < nc; ++j) {
             if (dist) {
                 dev::d2d(st, xfull->as<double>() + R0, V + (size_t)j * N, (size_t)N * 8);
@@ -107,21 +132,19 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
             dev::gs_pass(st, V, N, j + 1, w, N, d_h2, nullptr, d_n);
             dev::allreduce_sum(st, d_n, 1);
             dev::scale_inv_norm(st, w, d_n, V + (size_t)(j + 1) * N, N);
-        }
-        dev::d2h(st, hh.data() + (size_t)k * RW, d_tab + (size_t)k * RW, (size_t)(nc - k) * RW * 8);
-        dev::sync(st);
-        for (int j = k; j < nc; ++j) {
-            const double* r = hh.data() + (size_t)j * RW;
-            for (int i = 0; i <= j; ++i) {
-                const double c = r[i] + r[(ld + 1) + i];
-                T[(size_t)i * ld + j] = c;
-                T[(size_t)j * ld + i] = c;
+            /* On large superblocks (a matvec costs far more than a host round trip) the stopping test is also made inside the
+               cycle, after every step from the second new one on, instead of only at the restart boundary: saves the 4 or so
+               matvecs a converged solve would otherwise still run to fill the basis. */
+            if (early_test && j + 1 < nc && j >= k + 1) {
+                if (absorb_rows(j + 1)) break;
+                const int nj = j + 1;
+                std::vector<double> Tj((size_t)nj * nj), evj, Sj;
+                for (int a = 0; a < nj; ++a) for (int b = 0; b < nj; ++b) Tj[(size_t)a * nj + b] = T[(size_t)a * ld + b];
+                small_sym_eig(nj, Tj, evj, Sj);
+                if (std::fabs(beta_last * Sj[(size_t)(nj - 1) * nj + 0]) <= opts.tol * std::max(std::fabs(evj[0]), 1e-300)) { nc = nj; break; }
             }
-            const double b = std::sqrt(std::max(0.0, r[2 * (ld + 1)]));
-            beta_last = b;
-            /* invariant subspace reached at step j: what was queued after it worked on a null direction and is ignored */
-            if (!(b >= 1e-14)) { nc = j + 1; invariant = true; break; }
         }
+        if (!invariant) absorb_rows(nc);
         std::vector<double> Tm((size_t)nc * nc), ev, S;
         for (int i = 0; i < nc; ++i) for (int j = 0; j < nc; ++j) Tm[(size_t)i * nc + j] = T[(size_t)i * ld + j];
         small_sym_eig(nc, Tm, ev, S); /* ascending: the wanted pair is column 0 */

@@ -157,3 +157,19 @@ def test_exact_chain_sparse_workload_ground_state(P, ctx):
 
 def test_correlator_operator_products_match_dense(P, ctx, orc):
     pc.check_correlator_products(P, orc, ctx, J1J2_CYL)
+
+
+def test_in_cycle_stopping_test_of_the_eigensolver(P, ctx, orc, monkeypatch):
+    """The stopping test made inside a restart cycle (on by default only for large superblocks) gives the same eigenpair with
+    fewer matvecs than testing at the restart boundaries only."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, "heis_8x4", m=48)
+    monkeypatch.setenv("DMRGX_EARLY_TEST_MIN", "1000000000")
+    e0, psi0, st0 = wl.shell.EPSSolve(tol=1e-10)
+    monkeypatch.setenv("DMRGX_EARLY_TEST_MIN", "1")
+    e1, psi1, st1 = wl.shell.EPSSolve(tol=1e-10)
+    assert st0["converged"] and st1["converged"]
+    assert abs(e0 - e1) <= 1e-9 * abs(e0) and abs(abs(psi0.get() @ psi1.get()) - 1.0) < 1e-6
+    assert st1["nmatvec"] <= st0["nmatvec"] and st1["resid"] <= 1e-10 * abs(e1)
+    x = psi1.get()
+    assert abs(x @ wl.shell.MatMult_host(x) - e1) < 1e-9
