@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <unordered_map>
 #include <cstdio>
@@ -69,6 +70,11 @@ struct Stream {
     std::map<size_t, std::vector<void*>> free_lists; /* caching allocator: size class -> free blocks */
     std::unordered_map<void*, size_t> live;
     size_t bytes_reserved = 0;
+    std::vector<void*> slabs;    /* what was actually cudaMalloc'ed: blocks are carved from slabs and live on the free lists */
+    char* slab_ptr = nullptr;
+    size_t slab_left = 0;
+    double malloc_seconds = 0;   /* time spent in cudaMalloc by the caching allocator (DMRGX_TRACE prints it at the end) */
+    long long malloc_calls = 0;
     cudaEvent_t ev_main = nullptr;
     std::vector<cudaEvent_t> ev_lane;
     ncclComm_t comm = nullptr;
@@ -111,6 +117,8 @@ void destroy(Stream* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     cudaStreamSynchronize(st->s);
+    if (getenv("DMRGX_TRACE"))
+        fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved\n", st->malloc_calls, st->malloc_seconds, st->bytes_reserved / 1e9);
     if (st->solver) cusolverDnDestroy(st->solver);
     if (st->solver_work) cudaFree(st->solver_work);
     for (auto& l : st->lanes) {
@@ -122,8 +130,7 @@ void destroy(Stream* st) {
     for (auto& e : st->ev_lane) cudaEventDestroy(e);
     if (st->ev_main) cudaEventDestroy(st->ev_main);
     if (st->comm) comm_destroy_(st);
-    for (auto& kv : st->free_lists) for (void* q : kv.second) cudaFree(q);
-    for (auto& kv : st->live) cudaFree(kv.first);
+    for (void* q : st->slabs) cudaFree(q);
     cudaFree(st->partials);
     cudaFree(st->ticket);
     cudaFree(st->info);
@@ -156,16 +163,28 @@ void* malloc_bytes(Stream* st, size_t bytes) {
         st->live[p] = f->first;
         return p;
     }
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, cls);
-    if (e != cudaSuccess) { /* out of memory: give the cached blocks back and retry once */
-        cudaGetLastError();
-        cudaStreamSynchronize(st->s);
-        for (auto& kv : st->free_lists) { for (void* q : kv.second) cudaFree(q); kv.second.clear(); }
-        CUDA_OK(cudaMalloc(&p, cls));
+    /* a new block: carved from the current slab (1 GiB, or the block itself when larger); cudaMalloc is called once per slab —
+       1227 calls and 2 s of a 10 s run went into it when every new block was its own cudaMalloc */
+    constexpr size_t SLAB = (size_t)1 << 30;
+    const size_t need = (cls + 255) & ~(size_t)255;
+    if (st->slab_left < need) {
+        const size_t sz = std::max(SLAB, need);
+        void* slab = nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMalloc(&slab, sz);
+        if (e != cudaSuccess && sz > need) { cudaGetLastError(); e = cudaMalloc(&slab, need); if (e == cudaSuccess) { st->slabs.push_back(slab); st->bytes_reserved += need; st->live[slab] = cls; return slab; } }
+        st->malloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        st->malloc_calls++;
+        CUDA_OK(e);
+        st->slabs.push_back(slab);
+        st->slab_ptr = (char*)slab;
+        st->slab_left = sz;
+        st->bytes_reserved += sz;
     }
+    void* p = st->slab_ptr;
+    st->slab_ptr += need;
+    st->slab_left -= need;
     st->live[p] = cls;
-    st->bytes_reserved += cls;
     return p;
 }
 void free_bytes(Stream* st, void* p) {
