@@ -360,7 +360,8 @@ def main():
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "blocks read from disk (InitializeFromDisk layout)" if args.from_disk else "synthetic",
         "config": {"workload": "%s m=%d sweep-midpoint superblock H*psi, D=%d, T=%d shell terms" % (args.config, args.m, n, st["nterms"]),
-                   "l2": "operator panels (%.0f MB) exceed the 126 MB L2, no flush needed" % ((st["alg_bytes_global"] - 16 * n) / 1e6),
+                   "l2": "no flush needed: one apply streams through %.0f MB on this rank (V workspace + pre-summed factors + psi, plus %.0f MB of "
+                         "operator panels), more than the 126 MB L2" % (st["workspace_bytes"] / 1e6, (st["alg_bytes"] - 16 * n) / 1e6),
                    "parallelism": ("superblock rows sharded over %d GPUs (cuts %s), NCCL all-gather of psi per apply" % (world, cuts.tolist()))
                    if world > 1 else "single"},
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * (re_ - rb), "d2h_bytes_per_step": 8 * (re_ - rb), "ms_per_step": ms_e2e},

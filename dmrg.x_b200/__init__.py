@@ -346,10 +346,11 @@ class HShell:
         n, nt, t1, t2 = LL(), LL(), LL(), LL()
         ab, af = C.c_double(), C.c_double()
         _chk(lib().dmrgx_hshell_stats(self.h, C.byref(n), C.byref(nt), C.byref(ab), C.byref(af), C.byref(t1), C.byref(t2)))
-        gb, gf = C.c_double(), C.c_double()
+        gb, gf, wb = C.c_double(), C.c_double(), C.c_double()
         _chk(lib().dmrgx_hshell_stats_global(self.h, C.byref(gb), C.byref(gf)))
+        _chk(lib().dmrgx_hshell_workspace_bytes(self.h, C.byref(wb)))
         return dict(nstates=n.value, nterms=nt.value, alg_bytes=ab.value, alg_flops=af.value, tiles_stage1=t1.value, tiles_stage2=t2.value,
-                    alg_bytes_global=gb.value, alg_flops_global=gf.value)
+                    alg_bytes_global=gb.value, alg_flops_global=gf.value, workspace_bytes=wb.value)
 
     def MatMult(self, x, y):
         """MatMult(H, x, y) on device vectors (or raw device pointers as ints)"""

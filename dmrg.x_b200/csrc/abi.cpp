@@ -211,6 +211,15 @@ int dmrgx_hshell_apply_host(dmrgx_hshell h, const double* x, double* y) {
     });
 }
 int dmrgx_hshell_destroy(dmrgx_hshell h) { return guard([&] { if (h) { dev::sync(H(h)->ctx->st); delete H(h); } }); }
+/* device memory one apply streams through: the V workspace, the pre-summed right factors and psi in / out (the original
+   operator panels come on top); what decides whether the apply can live in L2 */
+int dmrgx_hshell_workspace_bytes(dmrgx_hshell h, double* bytes) {
+    HShell* s = H(h);
+    double b = 16.0 * (double)s->n + (s->work ? (double)s->work->bytes : 0.0);
+    for (const BufRef& k : s->keep) b += (double)k->bytes;
+    *bytes = b;
+    return 0;
+}
 int dmrgx_hshell_stats_global(dmrgx_hshell h, double* alg_bytes, double* alg_flops) {
     *alg_bytes = (double)H(h)->alg_bytes_global; *alg_flops = H(h)->alg_flops_global;
     return 0;

@@ -129,6 +129,8 @@ int dmrgx_hshell_destroy(dmrgx_hshell h);
 int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, double* alg_bytes, double* alg_flops,
                        dmrgx_int* ntiles_stage1, dmrgx_int* ntiles_stage2);
 
+/* bytes of device memory one apply streams through besides the original operator panels (V workspace, pre-summed factors, psi, y) */
+int dmrgx_hshell_workspace_bytes(dmrgx_hshell h, double* bytes);
 /* the algorithmic bytes / flops of the WHOLE operator on a multi-GPU context (dmrgx_hshell_stats then reports this rank's share) */
 int dmrgx_hshell_stats_global(dmrgx_hshell h, double* alg_bytes, double* alg_flops);
 
