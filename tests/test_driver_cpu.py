@@ -113,16 +113,19 @@ def test_checkpoint_format_and_restart(exe, orc, tmp_path):
     assert abs(t2[-1][-1] - (-5.142090632841)) < 1e-9
 
 
-def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path):
+@pytest.mark.parametrize("int_bytes", [4, 8], ids=["petscint32", "petscint64"])
+def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path, int_bytes):
     """BASELINE configs[4]: blocks saved by the driver are read back through Block.InitializeFromDisk and the sweep-midpoint
     superblock built from them has the energy the driver reported for that step."""
     import json
     import dmrgx_loader
     import bench_workload as W
     args = ["-Lx", "4", "-Ly", "4", "-J1", "0.5", "-Jz1", "1", "-J2", "0.25", "-Jz2", "0.5", "-mwarmup", "24", "-msweeps", "32", "-H_eps_tol", "1e-12",
-            "-do_correlators", "0", "-scratch_dir", str(tmp_path) + "/s/", "-data_dir", str(tmp_path) + "/d/"]
+            "-do_correlators", "0", "-scratch_dir", str(tmp_path) + "/s/", "-data_dir", str(tmp_path) + "/d/", "-petsc_int_bytes", str(int_bytes)]
     r = subprocess.run([exe] + args, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-1500:]
+    info = dict(l.split() for l in open(str(tmp_path) + "/s/Sweep_000000001/Sys_000000006/BlockInfo.dat"))
+    assert info["NumBytesPetscInt"] == str(int_bytes)
     P = dmrgx_loader.load_package()
     P.use_library(os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
     try:
