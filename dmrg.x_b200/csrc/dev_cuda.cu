@@ -277,6 +277,25 @@ struct Stager {
    and no multiply in the inner loop (the plan folds the couplings into the right factors, so this is where the flops
    are).  Otherwise the generic variant: fragment counts and the coefficient are runtime values.  Two variants per
    operand layout keep the kernel small enough for the instruction caches. */
+/* the DMMAs of one 16-deep chunk for a warp that owns NMI x NNI fragments */
+template <bool A_MK, bool B_NK, bool UNIT, int NMI, int NNI>
+__device__ __forceinline__ void chunk_mma(double (&acc)[4][4][2], const double* as, const double* bs, double coef) {
+    constexpr int a_sm = A_MK ? S_MK : 1, a_sk = A_MK ? 1 : S_KM;
+    constexpr int b_sn = B_NK ? S_MK : 1, b_sk = B_NK ? 1 : S_KM;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[NMI], b[NNI];
+#pragma unroll
+        for (int mi = 0; mi < NMI; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
+#pragma unroll
+        for (int ni = 0; ni < NNI; ++ni) b[ni] = UNIT ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
+#pragma unroll
+        for (int ni = 0; ni < NNI; ++ni)
+#pragma unroll
+            for (int mi = 0; mi < NMI; ++mi) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
 template <bool A_MK, bool B_NK, bool FULL, bool UNIT>
 __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                              int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
@@ -309,18 +328,20 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
         __syncthreads();
         const double* as = As + cur * SMEM_TILE + a_base;
         const double* bs = Bs + cur * SMEM_TILE + b_base;
-#pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[4], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = UNIT ? bs[ni * 8 * b_sn + kk * 4 * b_sk] : bs[ni * 8 * b_sn + kk * 4 * b_sk] * coef;
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-                    if (FULL || (mi < nmi && ni < nni)) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        if (FULL) {
+            chunk_mma<A_MK, B_NK, UNIT, 4, 4>(acc, as, bs, coef);
+        } else {
+            /* ragged tile: the fragment counts of this warp select a body compiled for exactly that many DMMAs — a predicated-off
+               DMMA still occupies the tensor pipe (a 32x32 tile took as long as a 64x64 one) */
+#define MMA_CASE(M_, N_) case (M_) * 5 + (N_): chunk_mma<A_MK, B_NK, UNIT, M_, N_>(acc, as, bs, coef); break;
+            switch (nmi * 5 + nni) {
+                MMA_CASE(4, 4) MMA_CASE(4, 3) MMA_CASE(4, 2) MMA_CASE(4, 1)
+                MMA_CASE(3, 4) MMA_CASE(3, 3) MMA_CASE(3, 2) MMA_CASE(3, 1)
+                MMA_CASE(2, 4) MMA_CASE(2, 3) MMA_CASE(2, 2) MMA_CASE(2, 1)
+                MMA_CASE(1, 4) MMA_CASE(1, 3) MMA_CASE(1, 2) MMA_CASE(1, 1)
+                default: break;
+            }
+#undef MMA_CASE
         }
         __syncthreads();
     }
