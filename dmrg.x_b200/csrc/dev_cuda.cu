@@ -1,13 +1,19 @@
 /*  dev_cuda.cu — hand-written sm_100a kernels behind dev.h.
  *
- *  Hot kernel: chain_kernel — one CTA per 64×64 (or smaller) output tile, 4 warps in a 2×2 grid, each
- *  warp a 32×32 sub-tile held as 4×4 FP64 DMMA (mma.sync.m8n8k4.f64) accumulator fragments.  Operand
- *  chunks of 16 in K are staged global→shared with cp.async (LDGSTS.64, zero-filled at the ragged
- *  edges), double-buffered; the shared layouts are padded (row stride ≡ 4 mod 16 doubles) so that both
- *  the row-major and the transposed fragment reads are bank-conflict-free.  FP64 has no tcgen05/UMMA
- *  kind, so DMMA through mma.sync is the Blackwell tensor path for this arithmetic.
- *  Sparse (CSR) and scaled-identity factors are accumulated into the same register tile by the
- *  coalesced slow-path segments, so every output element is written exactly once per launch.
+ *  chain_kernel — the one compute engine of the path (H·psi stages 1 and 2, rho = X·Xᵀ, O·Uᵀ, U·T, enlarged H, operator
+ *  products).  One CTA per ≤64×64 output tile, 4 warps in a 2×2 grid, each warp up to a 32×32 sub-tile held as 4×4 FP64 DMMA
+ *  (mma.sync.m8n8k4.f64) accumulator fragments; a tile accumulates its whole chain of segments in registers and is written
+ *  once.  Operand chunks of 16 in K are staged global→shared with cp.async (LDGSTS.64, K tail by the zero-fill size operand,
+ *  rows of ragged tiles clamped), double-buffered; the shared layouts are padded (row stride ≡ 4 mod 16 doubles) so that both
+ *  the row-major and the transposed fragment reads are bank-conflict-free, and the layouts are template parameters so every
+ *  LDS offset is an immediate.  FP64 has no tcgen05/UMMA kind, so DMMA through mma.sync is the Blackwell tensor path for
+ *  this arithmetic.  A predicated-off DMMA still occupies the tensor pipe for its 16 cycles, so ragged tiles
+ *  dispatch per chunk to a body compiled for exactly the warp's fragment counts (profiles/r1_chain_kernel.md).
+ *  Sparse (CSR), AXPY and scaled-identity factors are accumulated into the same register tile by slow-path segments.
+ *
+ *  Also here: gs_pass_kernel (fused Gram-Schmidt passes of the Lanczos solver, HBM-bound, deterministic last-block
+ *  reductions), jacobi_eig_kernel (batched eigensolver for reduced-density-matrix blocks of up to 64 states), the solver
+ *  lanes around cuSOLVER for larger blocks, the NCCL collectives (bound lazily) and the slab-based caching allocator.
  */
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
