@@ -207,3 +207,24 @@ def check_correlator_products(P, orc, ctx, ham):
         L.dmrgx_hshell_destroy(h)
         ref = expect_dense(lops, rops)
         assert abs(v.value - ref) < 1e-12, (lops, rops, v.value, ref)
+
+
+def check_testkron01_kronblocks(P, ctx, golden_dir):
+    """KronBlocks_t bookkeeping of the product against the reference's own golden case (tests/UnitTests_DMRGKron.cpp:39-252,
+    TestKron01): left sectors {+.5:2, -.5:1}, right sectors {+1:1, 0:2, -1:1}, all sectors kept (IL-major, stable sort by
+    descending total QN, include/DMRGKron.hpp:147-158)."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(golden_dir, "testkron01.json")))
+    L = P.Block.Initialize(ctx, fx["blocks"]["Left"]["nsites"], fx["blocks"]["Left"]["qn"], fx["blocks"]["Left"]["sizes"])
+    R = P.Block.Initialize(ctx, fx["blocks"]["Right"]["nsites"], fx["blocks"]["Right"]["qn"], fx["blocks"]["Right"]["sizes"])
+    kb = P.KronBlocks(L, R, [])
+    q, il, ir, size, off = kb.data()
+    assert list(zip(q.tolist(), il.tolist(), ir.tolist(), size.tolist())) == [
+        (1.5, 0, 0, 2), (0.5, 0, 1, 4), (0.5, 1, 0, 1), (-0.5, 0, 2, 2), (-0.5, 1, 1, 2), (-1.5, 1, 2, 1)]
+    assert off.tolist() == [0, 2, 6, 7, 9, 11, 12] and kb.NumStates() == 12 and kb.size() == 6
+    assert kb.Map(1, 1) == 4 and kb.Map(2, 0) == -1 and kb.Offsets(5, 5) == -1 and kb.Offsets(0, 1) == 2
+    # one target sector: IL-major order, not sorted (include/DMRGKron.hpp:160-171)
+    k0 = P.KronBlocks(L, R, [0.5])
+    q, il, ir, size, off = k0.data()
+    assert list(zip(il.tolist(), ir.tolist(), size.tolist())) == [(0, 1, 4), (1, 0, 1)] and off.tolist() == [0, 4, 5]

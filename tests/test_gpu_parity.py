@@ -169,3 +169,7 @@ def test_exact_chain_sparse_workload_ground_state(P, ctx):
 
 def test_correlator_operator_products_match_dense(P, ctx, orc):
     pc.check_correlator_products(P, orc, ctx, J1J2_CYL)
+
+
+def test_testkron01_kronblocks_golden(P, ctx, golden_dir):
+    pc.check_testkron01_kronblocks(P, ctx, golden_dir)

@@ -173,3 +173,7 @@ def test_in_cycle_stopping_test_of_the_eigensolver(P, ctx, orc, monkeypatch):
     assert st1["nmatvec"] <= st0["nmatvec"] and st1["resid"] <= 1e-10 * abs(e1)
     x = psi1.get()
     assert abs(x @ wl.shell.MatMult_host(x) - e1) < 1e-9
+
+
+def test_testkron01_kronblocks_golden(P, ctx, golden_dir):
+    pc.check_testkron01_kronblocks(P, ctx, golden_dir)
