@@ -13,6 +13,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -250,12 +251,13 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
             if (pair_cost) (*pair_cost)[p] += H->stage1.flops - flops_before;
         }
     }
-    {   /* dry run to learn the total stage-2 work, then cut long chains so that the launch has ~5 waves of
+    {   /* dry run to learn the total stage-2 work, then cut long chains so that the launch has about two waves of
            equal items on 148 SMs x 3 resident CTAs (v0 lost a third of the machine to a 1.4-wave tail) */
         Plan probe;
         for (int p = 0; p < np; ++p)
             emit_cells(probe, yoff(kron->off[p]), true, SR.size[kron->pairs[p].ir], lr1[p] - lr0[p], SR.size[kron->pairs[p].ir], ycontrib[p], true);
-        const double target_items = 148.0 * 3.0 * 5.0;
+        const char* tgt = getenv("DMRGX_STAGE2_WAVES"); /* experiment hook */
+        const double target_items = 148.0 * 3.0 * (tgt ? atof(tgt) : 2.0); /* 2 waves: more parts only add partial-tile traffic (profiles/) */
         if (probe.flops > 0 && (double)probe.items.size() < target_items) H->stage2.split_item_cost = 0.5 * probe.flops / target_items;
     }
     for (int p = 0; p < np; ++p) {
