@@ -256,8 +256,13 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
         Plan probe;
         for (int p = 0; p < np; ++p)
             emit_cells(probe, yoff(kron->off[p]), true, SR.size[kron->pairs[p].ir], lr1[p] - lr0[p], SR.size[kron->pairs[p].ir], ycontrib[p], true);
-        const char* tgt = getenv("DMRGX_STAGE2_WAVES"); /* experiment hook */
-        const double target_items = 148.0 * 3.0 * (tgt ? atof(tgt) : 2.0); /* 2 waves: more parts only add partial-tile traffic (profiles/) */
+        /* How many work items the launch should have: one wave of the 444 resident CTAs for light superblocks, up to three for
+           heavy ones (about one item per 40 full-tile chunks of work).  Parts of a cut chain go through the scratch buffer and
+           the reduce pass, so more parts than needed to even out the last wave only add traffic: measured optima were 574 items
+           at m = 512, 858 at m = 1024 and 2012 at m = 2048 (profiles/r1_chain_kernel.md). */
+        const char* tgt = getenv("DMRGX_STAGE2_WAVES"); /* experiment hook: fixed number of waves */
+        const double chunks_total = probe.flops / (2.0 * 64 * 64 * 16);
+        const double target_items = tgt ? 444.0 * atof(tgt) : std::min(3.0 * 444.0, std::max(444.0, chunks_total / 40.0));
         if (probe.flops > 0 && (double)probe.items.size() < target_items) H->stage2.split_item_cost = 0.5 * probe.flops / target_items;
     }
     for (int p = 0; p < np; ++p) {
