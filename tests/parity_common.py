@@ -228,3 +228,41 @@ def check_testkron01_kronblocks(P, ctx, golden_dir):
     k0 = P.KronBlocks(L, R, [0.5])
     q, il, ir, size, off = k0.data()
     assert list(zip(il.tolist(), ir.tolist(), size.tolist())) == [(0, 1, 4), (1, 0, 1)] and off.tolist() == [0, 4, 5]
+
+
+def check_step_fixture(P, ctx, golden_dir):
+    """The product against the frozen step of tests/golden/step_j1j2_4x4.json (made by tests/golden/make_step_golden.py with the
+    oracle): bookkeeping bit-exact, H·x to 1e-13, E0 and truncation errors to 1e-10, kept-state counts exact."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(golden_dir, "step_j1j2_4x4.json")))
+    ham = fx["ham"]
+    blk = P.Block.Initialize(ctx, fx["nsites"], fx["qn"], fx["sizes"])
+    for i in range(fx["nsites"]):
+        for name, code in (("Sz", P.OpSz), ("Sp", P.OpSp)):
+            o = fx["ops"]["%s%d" % (name, i)]
+            blk.set_operator(code, i, o["rowptr"], o["col"], o["val"])
+    o = fx["ops"]["H"]
+    blk.set_operator(P.OpH, 0, o["rowptr"], o["col"], o["val"])
+    T = lambda n: P.HamiltonianTerms(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, ham["bcx"], ham["bcy"])
+    enl = P.KronEye_Explicit(blk, P.Block.SingleSite(ctx), T(8))
+    q, s = enl.sectors()
+    assert q.tolist() == fx["enlarged"]["qn"] and s.tolist() == fx["enlarged"]["sizes"]
+    kb = P.KronBlocks(enl, enl, [0.0])
+    kq, il, ir, size, off = kb.data()
+    k = fx["kron"]
+    assert (kq.tolist(), il.tolist(), ir.tolist(), size.tolist(), off.tolist()) == (k["qn"], k["il"], k["ir"], k["size"], k["off"])
+    H = kb.KronSumConstruct(T(16))
+    x = np.array(fx["x"]); y_ref = np.array(fx["y"])
+    y = H.MatMult_host(x)
+    assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * H.stats()["nterms"]
+    e0, psi, st = H.EPSSolve(tol=1e-12)
+    assert st["converged"] and abs(e0 - fx["e0"]) <= ENERGY_RTOL * abs(fx["e0"])
+    assert abs(abs(psi.get() @ np.array(fx["psi"])) - 1.0) < 1e-8
+    btL, btR = P.GetTruncation(kb, ctx.vec(len(fx["psi"]), fx["psi"]), fx["mstates"])
+    for bt, ref in ((btL, fx["trunc"]["L"]), (btR, fx["trunc"]["R"])):
+        bq, bs = bt.sectors()
+        assert bq.tolist() == ref["qn"] and bs.tolist() == ref["sizes"]
+        assert abs(bt.TruncErr - ref["err"]) <= ENERGY_RTOL * max(abs(ref["err"]), 1e-4)
+        ev = np.sort(bt.spectrum()[0])[::-1]
+        assert np.abs(ev - np.array(ref["spectrum"])).max() <= 1e-12

@@ -103,3 +103,28 @@ def test_symeig_matches_numpy(orc):
         wn = np.linalg.eigvalsh(A)[::-1]
         assert np.allclose(w, wn, atol=1e-12)
         assert np.allclose(A @ V, V * w, atol=1e-11)
+
+
+def test_oracle_reproduces_frozen_step(orc, golden_dir):
+    """tests/golden/step_j1j2_4x4.json (tests/golden/make_step_golden.py) guards the oracle against drift: rebuilt from the stored
+    input block, the oracle gives the same H·x, energy and truncation."""
+    O = orc
+    fx = json.load(open(os.path.join(golden_dir, "step_j1j2_4x4.json")))
+    ham = fx["ham"]
+    blk = O.Block.create(fx["nsites"], fx["qn"], fx["sizes"])
+    for i in range(fx["nsites"]):
+        for name, code in (("Sz", O.OP_SZ), ("Sp", O.OP_SP)):
+            o = fx["ops"]["%s%d" % (name, i)]
+            blk.set_op(code, i, np.array(o["rowptr"]), np.array(o["col"]), np.array(o["val"]))
+    o = fx["ops"]["H"]
+    blk.set_op(O.OP_H, 0, np.array(o["rowptr"]), np.array(o["col"]), np.array(o["val"]))
+    T = lambda n: O.ham_terms(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, ham["bcx"], ham["bcy"])
+    enl = O.kron_eye(blk, O.Block.single_site(), T(8))
+    kb = O.KronBlocks(enl, enl, [0.0])
+    sh = O.Shell(kb, T(16))
+    y = sh.apply(np.array(fx["x"]))
+    assert np.abs(y - np.array(fx["y"])).max() <= 1e-14 * np.abs(y).max()
+    e0, psi, _, _ = sh.eigs(tol=1e-13)
+    assert abs(e0 - fx["e0"]) <= 1e-11 * abs(e0)
+    tL = O.Truncation(kb, np.array(fx["psi"]), fx["mstates"], True)
+    assert tL.sectors()[1].tolist() == fx["trunc"]["L"]["sizes"] and abs(tL.trunc_err - fx["trunc"]["L"]["err"]) < 1e-13

@@ -177,3 +177,7 @@ def test_in_cycle_stopping_test_of_the_eigensolver(P, ctx, orc, monkeypatch):
 
 def test_testkron01_kronblocks_golden(P, ctx, golden_dir):
     pc.check_testkron01_kronblocks(P, ctx, golden_dir)
+
+
+def test_frozen_step_fixture(P, ctx, golden_dir):
+    pc.check_step_fixture(P, ctx, golden_dir)
