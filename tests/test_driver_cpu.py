@@ -147,3 +147,46 @@ def test_spin_one_chain_matches_oracle(exe, orc, tmp_path):
     ref, _ = dc.compare_with_oracle(orc, docs, dict(Lx=8, Ly=1, heisenberg=1.0, bcx=0, bcy=0, spin_twice=2), 27, [40])
     # kept-state counts inside degenerate SU(2) multiplets may differ after the first tie; the converged energy may not
     assert abs(docs["DMRGSteps"]["table"][-1][-1] - ref[-1]["GSEnergy"]) <= 1e-9 * abs(ref[-1]["GSEnergy"])
+
+
+def test_block_files_are_validated(exe, tmp_path):
+    """InitializeFromDisk refuses what the reference refuses (src/DMRGBlock.cpp:256-276, 330-341): missing files, wrong scalar
+    size, wrong sector count — and a .mat file that is not a PETSc binary matrix."""
+    import shutil
+    import dmrgx_loader
+    args = ["-Lx", "8", "-Ly", "1", "-heisenberg", "1", "-BCopen", "-mwarmup", "8", "-do_correlators", "0", "-scratch_dir", str(tmp_path) + "/s/",
+            "-data_dir", str(tmp_path) + "/d/"]
+    assert subprocess.run([exe] + args, capture_output=True, text=True).returncode == 0
+    src = str(tmp_path) + "/s/Sweep_000000000/Sys_000000002/"
+    P = dmrgx_loader.load_package()
+    P.use_library(os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
+    try:
+        ctx = P.Context(0)
+        good = P.Block.InitializeFromDisk(ctx, src)
+        assert good.NumSites() == 3 and good.CheckOperatorBlocks() == 0
+
+        def broken(name, edit):
+            dst = str(tmp_path) + "/" + name + "/"
+            shutil.copytree(src, dst)
+            edit(dst)
+            return dst
+        d1 = broken("nofile", lambda d: os.remove(d + "Sp_000000001.mat"))
+        with pytest.raises(Exception):
+            P.Block.InitializeFromDisk(ctx, d1)
+        d2 = broken("scalar", lambda d: open(d + "BlockInfo.dat", "w").write(open(src + "BlockInfo.dat").read().replace("NumBytesPetscScalar            8", "NumBytesPetscScalar            16")))
+        with pytest.raises(P.DmrgxError):
+            P.Block.InitializeFromDisk(ctx, d2)
+        d3 = broken("classid", lambda d: open(d + "Sz_000000000.mat", "r+b").write(b"\\x00\\x00\\x00\\x01"))
+        with pytest.raises(P.DmrgxError):
+            P.Block.InitializeFromDisk(ctx, d3)
+        # the C++ reader, through -restart_dir: a truncated QuantumNumbers.dat stops the run with an error
+        bad = str(tmp_path) + "/s_bad/"
+        shutil.copytree(str(tmp_path) + "/s/", bad)
+        q = bad + "Sweep_000000000/Sys_000000001/QuantumNumbers.dat"
+        first = open(q).read().splitlines()[0]
+        open(q, "w").write(first + "\n")
+        r = subprocess.run([exe, "-restart_dir", bad, "-msweeps", "8", "-data_dir", str(tmp_path) + "/d2/"], capture_output=True, text=True)
+        assert r.returncode != 0 and "QuantumNumbers.dat" in r.stderr
+        ctx.close()
+    finally:
+        P.use_library(None)
