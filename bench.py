@@ -142,7 +142,11 @@ def cpu_baseline(wl, seconds, kind_note=""):
     return {"value": st["alg_bytes"] / full_seconds / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
             "sample": "rows [%d,%d) of %d (%.3g%% of the superblock), %.2f s measured, scaled by rows; unfactored FMAs/row %.3g; setup %.1f s"
                       % (r0, r1, n, 100.0 * (r1 - r0) / n, dt, fmas / (r1 - r0), time.time() - t0 - dt),
-            "seconds_per_apply_extrapolated": full_seconds}
+            "seconds_per_apply_extrapolated": full_seconds,
+            # the reference's unfactored loop nest pays nz_L*nz_R multiply-adds per row per term (src/DMRGKron.cpp:1844-1864):
+            # its flop count per apply next to the factored count of our arm separates the algorithmic from the hardware speed-up
+            "unfactored_flops_per_apply": 2.0 * fmas / (r1 - r0) * n, "factored_flops_per_apply": st["alg_flops"],
+            "gflops": 2.0 * fmas / dt / 1e9}
 
 
 def main():
