@@ -23,7 +23,6 @@ OpSm, OpSz, OpSp, OpEye, OpH = -1, 0, 1, 2, 3
 
 LL = C.c_longlong
 _lib = None
-_lib_path = None
 
 
 class DmrgxError(RuntimeError):
@@ -40,17 +39,10 @@ class EigsStats(C.Structure):
     _fields_ = [("nmatvec", LL), ("nrestart", LL), ("converged", LL), ("resid", C.c_double)]
 
 
-def use_library(path):
-    """Select the shared library (tests point this at the plan-check build on CPU-only machines)."""
-    global _lib, _lib_path
-    _lib = None
-    _lib_path = path
-
-
 def lib():
     global _lib
     if _lib is None:
-        path = _lib_path or LIB_PATH
+        path = LIB_PATH   # the CUDA library next to this file and nothing else (tests/libswitch.py re-points it for CPU-only host-logic tests)
         if not os.path.exists(path):
             raise DmrgxError(100, "%s is missing: build it with __graft_entry__.build() (there is no CPU fallback)" % path)
         L = C.CDLL(path)

@@ -20,11 +20,14 @@ int guard(F&& f) {
     catch (const std::exception& e) { g_msg = e.what(); return 1; }
     catch (...) { g_msg = "unknown error"; return 1; }
 }
-inline Ctx* C(dmrgx_ctx c) { return (Ctx*)c; }
-inline Block* B(dmrgx_block b) { return (Block*)b; }
-inline Kron* K(dmrgx_kron k) { return (Kron*)k; }
-inline HShell* H(dmrgx_hshell h) { return (HShell*)h; }
-inline XForm* X(dmrgx_xform x) { return (XForm*)x; }
+/* Every handle leads to its context; the context's device is made current on the way in, so that a process may hold
+   contexts on several devices (allocations and launches of a context must never land on another context's GPU). */
+inline Ctx* cur(Ctx* c) { if (c && c->st) dev::make_current(c->st); return c; }
+inline Ctx* C(dmrgx_ctx c) { return cur((Ctx*)c); }
+inline Block* B(dmrgx_block b) { if (b) cur(((Block*)b)->ctx); return (Block*)b; }
+inline Kron* K(dmrgx_kron k) { if (k) cur(((Kron*)k)->ctx); return (Kron*)k; }
+inline HShell* H(dmrgx_hshell h) { if (h) cur(((HShell*)h)->ctx); return (HShell*)h; }
+inline XForm* X(dmrgx_xform x) { if (x) cur(((XForm*)x)->ctx); return (XForm*)x; }
 std::vector<Term> terms_of(dmrgx_int n, const double* a, const int* iop, const dmrgx_int* isite, const int* jop, const dmrgx_int* jsite) {
     std::vector<Term> t;
     for (dmrgx_int i = 0; i < n; ++i) t.push_back({a[i], iop[i], isite[i], jop[i], jsite[i]});
@@ -338,20 +341,29 @@ int dmrgx_selftest_gemm(dmrgx_ctx cx, dmrgx_int M, dmrgx_int N, dmrgx_int K, int
         for (int r = 0; r < reps; ++r) plan.run(ctx);
         dev::sync(ctx->st);
         *ms = (Trace::now() - t0) * 1e3 / std::max(1, reps);
-        /* spot check of one element against a host dot product */
-        std::vector<double> ha((size_t)M * K * nseg), hb((size_t)N * K * nseg), hc(1);
+        /* every element (or, for large products, every 7th row x every 5th column plus the last rows / columns of the ragged
+           edge) against host dot products of the same operands */
+        std::vector<double> ha((size_t)M * K * nseg), hb((size_t)N * K * nseg), hc((size_t)M * N);
         dev::d2h(ctx->st, ha.data(), A->p, ha.size() * 8); dev::d2h(ctx->st, hb.data(), B->p, hb.size() * 8);
-        const long long i = M / 3, j = N / 5;
-        dev::d2h(ctx->st, hc.data(), Cc->as<double>() + i * N + j, 8);
+        dev::d2h(ctx->st, hc.data(), Cc->p, hc.size() * 8);
         dev::sync(ctx->st);
-        double ref = 0;
-        for (int sgi = 0; sgi < nseg; ++sgi)
-            for (long long k = 0; k < K; ++k) {
-                const double a = a_k_contig ? ha[(size_t)sgi * M * K + i * K + k] : ha[(size_t)sgi * M * K + k * M + i];
-                const double b = b_k_contig ? hb[(size_t)sgi * N * K + j * K + k] : hb[(size_t)sgi * N * K + k * N + j];
-                ref += a * b;
+        const bool full = (double)M * (double)N * (double)K * nseg <= 5e8;
+        double worst = 0;
+        for (long long i = 0; i < M; ++i) {
+            if (!full && i % 7 != 0 && i < M - 20) continue;
+            for (long long j = 0; j < N; ++j) {
+                if (!full && j % 5 != 0 && j < N - 20) continue;
+                double ref = 0;
+                for (int sgi = 0; sgi < nseg; ++sgi) {
+                    const double* pa = ha.data() + (size_t)sgi * M * K;
+                    const double* pb = hb.data() + (size_t)sgi * N * K;
+                    for (long long k = 0; k < K; ++k)
+                        ref += (a_k_contig ? pa[i * K + k] : pa[k * M + i]) * (b_k_contig ? pb[j * K + k] : pb[k * N + j]);
+                }
+                worst = std::max(worst, std::fabs(ref - hc[(size_t)i * N + j]));
             }
-        *max_err = std::fabs(ref - hc[0]);
+        }
+        *max_err = worst;
     });
 }
 

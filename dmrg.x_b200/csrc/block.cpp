@@ -249,6 +249,11 @@ void block_set_operator(Block* b, int optype, int isite, const long long* rowptr
     const int shift = (optype == OP_SP) ? 1 : 0;
     const Sectors& S = b->sec;
     const int ns = S.nsec();
+    /* a malformed CSR (negative row lengths that still add up to nz in a .mat file, say) must not walk col[] / val[] out of
+       bounds: row pointers start at zero and never decrease */
+    if (rowptr[0] != 0) throw Err(ERR_ARG_CORRUPT, "CSR row pointers must start at 0.");
+    for (int r = 0; r < S.nstates(); ++r)
+        if (rowptr[r + 1] < rowptr[r]) throw Err(ERR_ARG_CORRUPT, "CSR row pointers must be non-decreasing.");
     dst->shift = shift;
     dst->tiles.assign(ns, {});
     dst->present = true;

@@ -63,6 +63,7 @@ int init(int device, void* user_stream, Stream** out); /* 0 on success; fails lo
 void destroy(Stream*);
 const char* last_error();
 int device_of(Stream*);
+void make_current(Stream*);   /* cudaSetDevice(device of the stream): called at every C-ABI entry point */
 void* raw_stream(Stream*);
 
 void* malloc_bytes(Stream*, size_t bytes);
@@ -122,6 +123,7 @@ void multiaxpy(Stream*, const double* V, long long ldv, int nvec, const double* 
 /* One fused Gram-Schmidt pass over the basis (a single read of V, deterministic reductions finished by the last block, no
    host involvement):   if d_coef:  w -= Σ_i d_coef[i]·V_i   (in place);   then, on the updated w,
    if d_dots: d_dots[i] = V_i·w (i < nvec);   if d_nrm2: *d_nrm2 = w·w.   nvec <= 40. */
+constexpr int MAX_BASIS = 39; /* largest ncv the fused kernels take (eigs_smallest validates -H_eps_ncv against it) */
 void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long long n, const double* d_coef, double* d_dots, double* d_nrm2);
 /* v = w / sqrt(*d_nrm2) */
 void scale_inv_norm(Stream*, const double* w, const double* d_nrm2, double* v, long long n);

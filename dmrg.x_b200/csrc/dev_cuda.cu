@@ -144,6 +144,7 @@ void destroy(Stream* st) {
     delete st;
 }
 int device_of(Stream* st) { return st->device; }
+void make_current(Stream* st) { cudaSetDevice(st->device); }
 void* raw_stream(Stream* st) { return (void*)st->s; }
 
 /* Caching allocator.  A DMRG sweep frees and allocates panels of slowly varying sizes every step; handing each one
@@ -1056,8 +1057,8 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         for (int b = 0; b < nblocks; ++b) if (n[b] > 0 && n[b] <= JAC_NMAX) jobs.push_back({d_A[b], d_w[b], n[b], 0});
         if (!jobs.empty()) {
             constexpr int smem = 2 * JAC_NMAX * JAC_LD * (int)sizeof(double);
-            static bool configured = false;
-            if (!configured) { CUDA_OK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+            /* a per-DEVICE attribute: set on every call (cheap), a process may hold contexts on several devices */
+            CUDA_OK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             JacobiJob* d_jobs = (JacobiJob*)malloc_bytes(st, jobs.size() * sizeof(JacobiJob));
             CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(JacobiJob), cudaMemcpyHostToDevice, st->s));
             jacobi_eig_kernel<<<(int)jobs.size(), JAC_THREADS, smem, st->s>>>(d_jobs);

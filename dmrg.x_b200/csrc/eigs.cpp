@@ -59,6 +59,8 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     const bool dist = ctx->world > 1;
     EigsStats stats;
     if (NG <= 0) throw Err(ERR_GENERIC, "empty superblock");
+    /* the fused Gram-Schmidt and Ritz-rotation kernels keep the whole basis of a cycle in registers: at most 39 vectors */
+    if (opts.ncv > dev::MAX_BASIS) throw Err(ERR_ARG_OUTOFRANGE, "-H_eps_ncv is limited to " + std::to_string(dev::MAX_BASIS) + " on this path (got " + std::to_string(opts.ncv) + ")");
     const int ld = (int)std::max<long long>(1, std::min<long long>(opts.ncv < 2 ? 2 : opts.ncv, NG));
     /* SLEPc default max_it = max(100, 2N/ncv) restarts */
     const long long max_it = opts.max_it > 0 ? opts.max_it : std::max<long long>(100, 2 * NG / ld);

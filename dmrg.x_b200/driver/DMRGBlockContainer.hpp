@@ -8,6 +8,7 @@
  *  the SLEPc EPS object becomes dmrgx_eigs_smallest with the `-H_eps_*` options.
  */
 #pragma once
+#include <unistd.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -80,6 +81,9 @@ public:
                 std::stringstream ss; ss << in.rdbuf();
                 o.InsertString(ss.str());
             }
+            /* the spin type of the saved blocks rules the sites added from now on (src/DMRGBlock.cpp:280-315): a conflicting -spin
+               is an error, a missing one is imposed — before SingleSite is created below */
+            ierr = BlockIO::ApplySpinTypeOfBlockDir(restart_dir + BlockDir("Sys", 0)); CHKERRQ(ierr);
             std::map<std::string, PetscInt> d;
             { std::ifstream in((restart_dir + "Sweep.dat").c_str()); for (std::string k; in >> k;) { PetscInt v; in >> v; d[k] = v; } }
             for (const char* k : {"GlobIdx", "LoopIdx", "num_sys_blocks", "sys_ninit"}) if (!d.count(k)) SETERRQ1(mpi_comm, 1, "Sweep.dat: %s not found.", k);
@@ -547,11 +551,17 @@ private:
     /** :2727-2764 — Hamiltonian.dat, PetscOptions.dat, Sweep.dat and (here) the blocks themselves, at the end of a completed loop */
     PetscErrorCode SaveSweepsData() {
         if (!do_save_blocks) return 0;
+        /* The blocks are replicated on every rank of a multi-GPU run: rank 0 alone writes the checkpoint (every rank writing
+           the same files would truncate what another had finished, and cost N device-to-host gathers). */
+        { int rank = 0, world = 1; dmrgx_ctx_rank(DmrgxContext(), &rank, &world); if (rank != 0) return 0; }
         PetscErrorCode ierr;
         int spin_type_key = 102; /* SpinOneHalf = 102, SpinOne = 101 (include/DMRGBlock.hpp:51-55) */
         { std::string sp; PetscBool set; PetscOptions::DB().GetString("-spin", sp, &set); if (set && sp == "1") spin_type_key = 101; }
         const std::string dir = scratch_dir + SweepDir(LoopIdx);
         ierr = Makedir(dir); CHKERRQ(ierr);
+        /* Sweep.dat is the commit marker -restart_dir looks for: an older one in this directory goes first, the new one is
+           written to a temporary name, flushed to disk and renamed into place after every block file is complete. */
+        remove((dir + "Sweep.dat").c_str());
         for (PetscInt iblock = 0; iblock < sys_ninit; ++iblock) {
             if (!sys_blocks[(size_t)iblock].Initialized()) continue;
             ierr = BlockIO::Save(sys_blocks[(size_t)iblock], dir + BlockDir("Sys", iblock), io_int_bytes, spin_type_key); CHKERRQ(ierr);
@@ -565,12 +575,21 @@ private:
                 if (set) f << key << " " << (v.empty() ? "yes" : v) << std::endl;
             }
         }
-        std::ofstream f((dir + "Sweep.dat").c_str());
-        const PetscInt num_env_blocks = 1, env_ninit = 0;
-#define SWEEP_DUMP(VAR) f << std::setw(20) << (#VAR) << "  " << (VAR) << "\n";
-        SWEEP_DUMP(GlobIdx); SWEEP_DUMP(LoopIdx); SWEEP_DUMP(num_sys_blocks); SWEEP_DUMP(num_env_blocks); SWEEP_DUMP(sys_ninit); SWEEP_DUMP(env_ninit);
-        SWEEP_DUMP(num_sites); SWEEP_DUMP(sweep_mode); SWEEP_DUMP(msweep_idx);
+        const std::string tmp = dir + "Sweep.dat.tmp";
+        {
+            FILE* f = fopen(tmp.c_str(), "w");
+            if (!f) SETERRQ1(mpi_comm, 1, "cannot write %s", tmp.c_str());
+            const PetscInt num_env_blocks = 1, env_ninit = 0;
+#define SWEEP_DUMP(VAR) fprintf(f, "%20s  %lld\n", #VAR, (long long)(VAR));
+            SWEEP_DUMP(GlobIdx); SWEEP_DUMP(LoopIdx); SWEEP_DUMP(num_sys_blocks); SWEEP_DUMP(num_env_blocks); SWEEP_DUMP(sys_ninit); SWEEP_DUMP(env_ninit);
+            SWEEP_DUMP(num_sites); SWEEP_DUMP(sweep_mode); SWEEP_DUMP(msweep_idx);
 #undef SWEEP_DUMP
+            fflush(f);
+            fsync(fileno(f));
+            fclose(f);
+        }
+        sync(); /* the block files reach the disk before the marker names them */
+        if (rename(tmp.c_str(), (dir + "Sweep.dat").c_str())) SETERRQ1(mpi_comm, 1, "cannot commit %sSweep.dat", dir.c_str());
         return 0;
     }
 

@@ -64,8 +64,19 @@ inline PetscErrorCode ReadMat(const std::string& file, PetscInt n_expected, std:
     if (get_int(is, int_bytes) != MAT_FILE_CLASSID) SETERRQ1(0, PETSC_ERR_ARG_WRONG, "%s is not a PETSc binary matrix (or was written with another PetscInt size)", file.c_str());
     const long long M = get_int(is, int_bytes), N = get_int(is, int_bytes), nz = get_int(is, int_bytes);
     if (M != n_expected || N != n_expected || nz < 0) SETERRQ1(0, PETSC_ERR_ARG_WRONG, "%s: matrix dimensions do not match the block", file.c_str());
+    { /* nz must fit in the file: header + M row lengths + nz columns + nz values */
+        is.seekg(0, std::ios::end);
+        const long long fsize = (long long)is.tellg();
+        is.seekg(4LL * int_bytes, std::ios::beg);
+        if (fsize < 4LL * int_bytes + M * int_bytes || (fsize - 4LL * int_bytes - M * int_bytes) / (int_bytes + 8) < nz)
+            SETERRQ1(0, PETSC_ERR_ARG_CORRUPT, "%s: file is shorter than its header says", file.c_str());
+    }
     rowptr.assign((size_t)M + 1, 0);
-    for (long long r = 0; r < M; ++r) rowptr[(size_t)r + 1] = rowptr[(size_t)r] + get_int(is, int_bytes);
+    for (long long r = 0; r < M; ++r) {
+        const long long len = get_int(is, int_bytes);
+        if (len < 0 || len > nz) SETERRQ1(0, PETSC_ERR_ARG_CORRUPT, "%s: invalid row length", file.c_str());
+        rowptr[(size_t)r + 1] = rowptr[(size_t)r] + len;
+    }
     if (rowptr[(size_t)M] != nz) SETERRQ1(0, PETSC_ERR_ARG_CORRUPT, "%s: row lengths do not add up to nz", file.c_str());
     col.resize((size_t)nz); val.resize((size_t)nz);
     for (long long e = 0; e < nz; ++e) col[(size_t)e] = get_int(is, int_bytes);
@@ -109,6 +120,34 @@ inline PetscErrorCode Save(const Block::SpinBase& blk, const std::string& dir_in
     return 0;
 }
 
+/** The spin type recorded in a block file against the -spin option (src/DMRGBlock.cpp:280-315): a mismatch is an error;
+    without -spin the file's type is imposed as the option, so that sites added later have the spin of the loaded blocks. */
+inline PetscErrorCode ApplySpinTypeKey(long long key) {
+    const char* from_file = key == 102 ? "1/2" : (key == 101 ? "1" : nullptr); /* SpinOneHalf = 102, SpinOne = 101 (include/DMRGBlock.hpp:51-55) */
+    if (!from_file) SETERRQ1(0, 1, "Input SpinTypeKey %lld not valid/implemented.", key);
+    std::string spin; PetscBool set;
+    PetscOptions::DB().GetString("-spin", spin, &set);
+    if (set) {
+        if (spin != "1/2" && spin != "1") SETERRQ1(0, 1, "Given -spin %s not valid/implemented.", spin.c_str());
+        if (spin != from_file) SETERRQ2(0, 1, "Given spin types from file (%s) and command line (%s) do not match", from_file, spin.c_str());
+    } else {
+        PetscOptions::DB().kv["-spin"] = from_file;
+    }
+    return 0;
+}
+/** SpinTypeKey of a block directory (BlockInfo.dat), applied as above: -restart_dir calls this BEFORE the single site is created */
+inline PetscErrorCode ApplySpinTypeOfBlockDir(const std::string& dir_in) {
+    std::string dir = dir_in;
+    if (dir.empty() || dir.back() != '/') dir += '/';
+    std::ifstream info((dir + "BlockInfo.dat").c_str());
+    if (!info) SETERRQ1(0, 1, "Error in reading %s", (dir + "BlockInfo.dat").c_str());
+    for (std::string line; std::getline(info, line);) {
+        std::istringstream iss(line); std::string k; long long v;
+        if (iss >> k >> v && k == "SpinTypeKey") return ApplySpinTypeKey(v);
+    }
+    SETERRQ(0, 1, "SpinTypeKey not found.");
+}
+
 /** InitializeFromDisk (src/DMRGBlock.cpp:214-372) */
 inline PetscErrorCode Load(Block::SpinBase& blk, const std::string& dir_in) {
     std::string dir = dir_in;
@@ -121,6 +160,7 @@ inline PetscErrorCode Load(Block::SpinBase& blk, const std::string& dir_in) {
     for (const char* k : {"NumBytesPetscInt", "NumBytesPetscScalar", "PetscUseComplex", "NumSites", "NumStates", "NumSectors"})
         if (!m.count(k)) SETERRQ1(0, 1, "BlockInfo.dat: %s not found.", k);
     if (!m.count("SpinTypeKey")) SETERRQ(0, 1, "SpinTypeKey not found.");
+    { PetscErrorCode e = ApplySpinTypeKey(m["SpinTypeKey"]); CHKERRQ(e); }
     const int int_bytes = (int)m["NumBytesPetscInt"];
     if (int_bytes != 4 && int_bytes != 8) SETERRQ1(0, 1, "Incompatible NumBytesPetscInt. Got %lld.", m["NumBytesPetscInt"]);
     if (m["NumBytesPetscScalar"] != 8) SETERRQ1(0, 1, "Incompatible NumBytesPetscScalar. Expected 8. Got %lld.", m["NumBytesPetscScalar"]);

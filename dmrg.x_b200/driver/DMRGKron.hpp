@@ -86,7 +86,12 @@ public:
     }
     PetscErrorCode KronSumSetShellMatrix(const PetscBool& do_shell_in) { do_shell = do_shell_in; return 0; }     /* :318 */
     PetscErrorCode KronSumSetRedistribute(const PetscBool& do_redistribute_in = PETSC_TRUE) { do_redistribute = do_redistribute_in; return 0; } /* :324 */
-    PetscErrorCode KronSumSetToleranceFromOptions() { return PetscOptions::DB().GetReal("-ks_tol", &ks_tol, NULL); } /* :332-337 */
+    /** :332-337.  In the reference -ks_tol reaches only the KronBlocks_t of the SUPERBLOCK (include/DMRGBlockContainer.hpp:1449)
+        and is read only by the explicit MPIAIJ construction (src/DMRGKron.cpp:1109-1112, 1449-1454), never by the shell
+        matvec; the KronBlocks_t inside KronEye_Explicit (src/DMRGKron.cpp:612) keeps the default 1e-16, which is what the
+        device enlargement applies (csrc/block.cpp).  With the shell form (the only one built here) the option therefore has
+        no effect on either side: it is parsed for compatibility and deliberately not forwarded. */
+    PetscErrorCode KronSumSetToleranceFromOptions() { return PetscOptions::DB().GetReal("-ks_tol", &ks_tol, NULL); }
 
 private:
     PetscInt GlobIdx;

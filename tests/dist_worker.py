@@ -8,6 +8,8 @@ import sys
 
 import numpy as np
 
+import libswitch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -23,7 +25,7 @@ def main():
     from oracle import oracle as O
     P = dmrgx_loader.load_package()
     lib_path = os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so")
-    P.use_library(lib_path)
+    libswitch.use_library(P, lib_path)
     L = P.lib()
 
     def np_view(ptr, n):

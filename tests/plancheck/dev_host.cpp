@@ -27,6 +27,7 @@ long long launch_count() { return g_launches; }
 int init(int device, void*, Stream** out) { *out = new Stream{device}; return 0; }
 void destroy(Stream* s) { delete s; }
 int device_of(Stream* s) { return s->device; }
+void make_current(Stream*) {}
 void* raw_stream(Stream*) { return nullptr; }
 void* malloc_bytes(Stream*, size_t b) { return std::malloc(b ? b : 8); }
 void free_bytes(Stream*, void* p) { std::free(p); }

@@ -6,6 +6,8 @@ import subprocess
 
 import pytest
 
+import libswitch
+
 import driver_common as dc
 
 ROOT = dc.ROOT
@@ -127,7 +129,7 @@ def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path, int_bytes):
     info = dict(l.split() for l in open(str(tmp_path) + "/s/Sweep_000000001/Sys_000000006/BlockInfo.dat"))
     assert info["NumBytesPetscInt"] == str(int_bytes)
     P = dmrgx_loader.load_package()
-    P.use_library(os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
+    libswitch.use_library(P, os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
     try:
         ctx = P.Context(0)
         W.CONFIGS["j1j2_4x4"] = dict(Lx=4, Ly=4, J1=0.5, Jz1=1.0, J2=0.25, Jz2=0.5, bcx=0, bcy=1)
@@ -138,7 +140,7 @@ def test_isolated_matvec_from_disk_saved_blocks(exe, tmp_path, int_bytes):
         assert abs(e - last[-1]) <= 1e-10 * abs(e)
         ctx.close()
     finally:
-        P.use_library(None)
+        libswitch.use_library(P, None)
 
 
 def test_spin_one_chain_matches_oracle(exe, orc, tmp_path):
@@ -159,7 +161,7 @@ def test_block_files_are_validated(exe, tmp_path):
     assert subprocess.run([exe] + args, capture_output=True, text=True).returncode == 0
     src = str(tmp_path) + "/s/Sweep_000000000/Sys_000000002/"
     P = dmrgx_loader.load_package()
-    P.use_library(os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
+    libswitch.use_library(P, os.path.join(ROOT, "tests", "plancheck", "libdmrgx_plancheck.so"))
     try:
         ctx = P.Context(0)
         good = P.Block.InitializeFromDisk(ctx, src)
@@ -189,4 +191,63 @@ def test_block_files_are_validated(exe, tmp_path):
         assert r.returncode != 0 and "QuantumNumbers.dat" in r.stderr
         ctx.close()
     finally:
-        P.use_library(None)
+        libswitch.use_library(P, None)
+
+
+def test_restart_takes_the_spin_type_from_the_block_files(exe, tmp_path):
+    """src/DMRGBlock.cpp:280-315: restarting a spin-1 checkpoint WITHOUT -spin imposes the file's SpinTypeKey as -spin (the
+    added sites must be spin-1 sites), and a contradicting -spin is an error."""
+    import json
+    ham = ["-Lx", "8", "-Ly", "1", "-heisenberg", "1", "-BCopen", "-H_eps_tol", "1e-12", "-do_correlators", "0"]
+    s = str(tmp_path) + "/s/"
+    r = subprocess.run([exe] + ham + ["-spin", "1", "-mwarmup", "27", "-msweeps", "30", "-scratch_dir", s, "-data_dir", str(tmp_path) + "/d1/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    info = dict(l.split() for l in open(s + "Sweep_000000001/Sys_000000002/BlockInfo.dat"))
+    assert info["SpinTypeKey"] == "101"
+    assert not os.path.exists(s + "Sweep_000000001/Sweep.dat.tmp") and os.path.exists(s + "Sweep_000000001/Sweep.dat")
+    r2 = subprocess.run([exe, "-restart_dir", s, "-msweeps", "40", "-H_eps_tol", "1e-12", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d2/"],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stdout[-1500:] + r2.stderr[-1500:]
+    r3 = subprocess.run([exe] + ham + ["-spin", "1", "-mwarmup", "27", "-msweeps", "30,40", "-data_dir", str(tmp_path) + "/d3/"], capture_output=True, text=True)
+    assert r3.returncode == 0
+    t2 = json.load(open(str(tmp_path) + "/d2/DMRGSteps.json"))["table"]
+    t3 = json.load(open(str(tmp_path) + "/d3/DMRGSteps.json"))["table"]
+    assert len(t2) > 0 and t2[-1][14] == t3[-1][14]          # three-state sites were added: same superblock dimension
+    assert abs(t2[-1][-1] - t3[-1][-1]) <= 1e-9 * abs(t3[-1][-1])
+    r4 = subprocess.run([exe, "-restart_dir", s, "-spin", "1/2", "-msweeps", "40", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d4/"],
+                        capture_output=True, text=True)
+    assert r4.returncode != 0 and "do not match" in r4.stderr
+
+
+def test_malformed_block_matrix_is_rejected(exe, tmp_path):
+    """a .mat whose row lengths are negative but still add up to nz, or whose nz exceeds the file, must be refused — not read
+    out of bounds (ReadMat / dmrgx_block_set_operator)."""
+    import shutil
+    import struct
+    args = ["-Lx", "8", "-Ly", "1", "-heisenberg", "1", "-BCopen", "-mwarmup", "8", "-do_correlators", "0", "-scratch_dir", str(tmp_path) + "/s/",
+            "-data_dir", str(tmp_path) + "/d/"]
+    assert subprocess.run([exe] + args, capture_output=True, text=True).returncode == 0
+    f = str(tmp_path) + "/s/Sweep_000000000/Sys_000000001/Sz_000000000.mat"
+    raw = bytearray(open(f, "rb").read())
+    M, nz = struct.unpack(">i", raw[4:8])[0], struct.unpack(">i", raw[12:16])[0]
+    lens = list(struct.unpack(">%di" % M, raw[16:16 + 4 * M]))
+    assert M >= 2 and nz >= 1
+
+    def restart_with(edit, name):
+        bad = str(tmp_path) + "/" + name + "/"
+        shutil.copytree(str(tmp_path) + "/s/", bad)
+        g = bad + "Sweep_000000000/Sys_000000001/Sz_000000000.mat"
+        b = bytearray(raw)
+        edit(b)
+        open(g, "wb").write(bytes(b))
+        return subprocess.run([exe, "-restart_dir", bad, "-msweeps", "8", "-do_correlators", "0", "-data_dir", bad + "out/"], capture_output=True, text=True)
+
+    def neg_rows(b):
+        l2 = list(lens); l2[0] += 2; l2[1] -= 2     # {a+2, b-2, ...}: still sums to nz, second row may go negative
+        if l2[1] >= 0:
+            l2[0] += l2[1] + 1; l2[1] = -1
+        b[16:16 + 4 * M] = struct.pack(">%di" % M, *l2)
+    r = restart_with(neg_rows, "neg")
+    assert r.returncode != 0 and ("invalid row length" in r.stderr or "row lengths" in r.stderr)
+    r = restart_with(lambda b: b.__setitem__(slice(12, 16), struct.pack(">i", nz + 1000000)), "huge")
+    assert r.returncode != 0 and "shorter than its header" in r.stderr

@@ -28,3 +28,36 @@ def test_j1j2_cylinder_6x4(orc, tmp_path):
     args = ["-Lx", 6, "-Ly", 4, "-J1", 0.5, "-Jz1", 1, "-J2", 0.25, "-Jz2", 0.5]
     docs, out = dc.run_driver(EXE, tmp_path, args, 32, [64])
     dc.compare_with_oracle(orc, docs, dict(Lx=6, Ly=4, J1=0.5, Jz1=1.0, J2=0.25, Jz2=0.5), 32, [64])
+
+
+def test_restart_and_initialize_from_disk_on_the_device(tmp_path):
+    """f-2 on the real executable: -scratch_dir checkpoints in the reference's on-disk format, -restart_dir continues from them
+    and reproduces the uninterrupted run; the saved Sys block read back through Block.InitializeFromDisk (BASELINE configs[4])
+    gives the sweep-midpoint energy the driver reported."""
+    import json
+    import subprocess
+    import dmrgx_loader
+    import bench_workload as W
+    ham = ["-Lx", "4", "-Ly", "4", "-J1", "0.5", "-Jz1", "1", "-J2", "0.25", "-Jz2", "0.5", "-H_eps_tol", "1e-12", "-do_correlators", "0"]
+    s1 = str(tmp_path) + "/s/"
+    r = subprocess.run([EXE] + ham + ["-mwarmup", "24", "-msweeps", "32", "-scratch_dir", s1, "-data_dir", str(tmp_path) + "/d1/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    r2 = subprocess.run([EXE, "-restart_dir", s1, "-msweeps", "48", "-H_eps_tol", "1e-12", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d2/"],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0 and "Loading blocks from file" in r2.stdout, r2.stdout[-1500:] + r2.stderr[-1500:]
+    r3 = subprocess.run([EXE] + ham + ["-mwarmup", "24", "-msweeps", "32,48", "-data_dir", str(tmp_path) + "/d3/"], capture_output=True, text=True)
+    assert r3.returncode == 0
+    t2 = json.load(open(str(tmp_path) + "/d2/DMRGSteps.json"))["table"]
+    t3 = json.load(open(str(tmp_path) + "/d3/DMRGSteps.json"))["table"]
+    assert len(t2) == 12
+    for a, b in zip(t2, t3[-12:]):
+        assert a[:15] == b[:15] and abs(a[-1] - b[-1]) <= 1e-10 * abs(b[-1])
+    # InitializeFromDisk -> enlarge -> superblock -> ground state == the energy of that step in the driver's table
+    P = dmrgx_loader.load_package()
+    ctx = P.Context(0)
+    W.CONFIGS["j1j2_4x4"] = dict(Lx=4, Ly=4, J1=0.5, Jz1=1.0, J2=0.25, Jz2=0.5, bcx=0, bcy=1)
+    wl = W.DiskWorkload(P, ctx, "j1j2_4x4", s1 + "Sweep_000000001/")
+    e, psi, st = wl.shell.EPSSolve(tol=1e-12)
+    last = json.load(open(str(tmp_path) + "/d1/DMRGSteps.json"))["table"][-1]
+    assert wl.m == last[8] and wl.n == last[14] and abs(e - last[-1]) <= 1e-10 * abs(e)
+    ctx.close()

@@ -4,6 +4,8 @@ truncation errors 1e-10 relative (north_star), bookkeeping bit-exact."""
 import os
 
 import numpy as np
+
+import libswitch
 import pytest
 
 import parity_common as pc
@@ -17,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def P():
     import dmrgx_loader
     P = dmrgx_loader.load_package()
-    P.use_library(None)  # the real CUDA library, nothing else
+    libswitch.use_library(P, None)  # the real CUDA library, nothing else
     return P
 
 
@@ -73,6 +75,93 @@ def test_synthetic_workload_matvec_matches_oracle(P, ctx, orc, config, m):
     pc.check_kron_bookkeeping(P, orc, wl.kron, kb_o)
     osh = orc.Shell(kb_o, wl.terms)
     pc.check_matvec(P, orc, ctx, wl.shell, osh, np.random.default_rng(3), nvec=2)
+
+
+def _row_windows(kron, nrows):
+    """>= 3 windows of superblock rows: across the start of the largest sector pair (ragged edge tile of the previous pair next
+    to full tiles), in its middle (full 64x64 tiles, long stage-2 chains that the planner may split), across its end."""
+    _, _, _, _, off = kron.data()
+    sizes = np.diff(off)
+    big = int(np.argmax(sizes))
+    n = int(off[-1])
+    h = nrows // 2
+    a, e = int(off[big]), int(off[big + 1])
+    mid = a + (e - a) // 2
+    return [(max(0, c - h), min(n, c + h)) for c in (a, mid, e)] + [(0, min(n, nrows))]
+
+
+@pytest.mark.parametrize("config,m,nrows", [("j1j2_12x6", 512, 2048), ("j1j2_12x6", 1024, 1024), ("j1j2_12x6", 2048, 384),
+                                            ("heis_8x4", 768, 1024), ("xy_16x8", 640, 1024)])
+def test_headline_tile_sizes_match_oracle_on_row_windows(P, ctx, orc, config, m, nrows):
+    """The code that runs the flops of the metric's configuration — full 64x64 unit-coefficient DMMA tiles, cells tiled into
+    several 64-wide items, K spanning many chunks, stage-2 chains split into parts + reduce_kernel — against the oracle's
+    restatement of MatMult_KronSumShell (src/DMRGKron.cpp:1844-1864) on windows of rows: largest enlarged sector > 64 at
+    m = 512 (~200), > 128 at m = 1024 (~400) and the metric's own m = 2048 (~800)."""
+    import bench_workload as W
+    import os as _os
+    wl = W.Workload(P, ctx, config, m=m)
+    q, s = wl.enl.sectors()
+    assert s.max() > 128
+    _, kb_o = W.oracle_side(orc, wl)
+    pc.check_kron_bookkeeping(P, orc, wl.kron, kb_o)
+    st = wl.shell.stats()
+    x = wl.random_state(9)
+    y = wl.shell.MatMult_host(x)
+    scale = np.abs(y).max()
+    cores = _os.cpu_count() or 1
+    worst = 0.0
+    for (r0, r1) in _row_windows(wl.kron, nrows):
+        y_ref = orc.Shell(kb_o, wl.terms, rows=(r0, r1)).apply(x, cores)
+        worst = max(worst, np.abs(y[r0:r1] - y_ref).max() / scale)
+    assert worst <= pc.MATVEC_RTOL * st["nterms"], worst
+    if m >= 2048:   # the planner did split stage-2 chains here (reduce_kernel in play)
+        assert st["tiles_stage2"] > 1000
+
+
+@pytest.mark.parametrize("m,keep", [(256, 200), (384, 300)])
+def test_truncation_and_rotation_match_oracle_at_larger_sectors(P, ctx, orc, m, keep):
+    """GetTruncation / RotateOperators with reduced-density-matrix blocks beyond the 64-state shared-memory solver (largest
+    block ~100 at m = 256, ~150 at m = 384): both sides get the SAME psi (the product's converged ground state), so the
+    kept-state counts, spectra and truncation errors are comparable bit for bit / to 1e-10."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, "heis_8x4", m=m)
+    enl_o, kb_o = W.oracle_side(orc, wl)
+    q, s = wl.enl.sectors()
+    assert s.max() > 64
+    e, psi, st = wl.shell.EPSSolve(tol=1e-11)
+    assert st["converged"]
+    ph = psi.get()
+    for keep in range(keep, keep + 8):   # move the cut off a degenerate multiplet (the oracle reports ties)
+        obtL = orc.Truncation(kb_o, ph, keep, True)
+        obtR = orc.Truncation(kb_o, ph, keep, False)
+        if not (obtL.tie or obtR.tie):
+            break
+    pbtL, pbtR = P.GetTruncation(wl.kron, psi, keep)
+    pc.check_truncation(P, orc, pbtL, obtL, None)
+    pc.check_truncation(P, orc, pbtR, obtR, None)
+    pnew = P.RotateOperators(wl.enl, pbtL)
+    Up = pbtL.RotMatT()
+    HL = enl_o.get_op_dense(orc.OP_H)
+    assert np.abs(pc.dense_op(pnew, P.OpH) - Up @ HL @ Up.T).max() < 1e-11 * max(1.0, np.abs(HL).max())
+    for i in wl.used[:3] + [wl.nsites_blk]:
+        for pop, oop in ((P.OpSp, orc.OP_SP), (P.OpSz, orc.OP_SZ)):
+            O_enl = enl_o.get_op_dense(oop, i)
+            assert np.abs(pc.dense_op(pnew, pop, i) - Up @ O_enl @ Up.T).max() < 1e-11
+    assert pnew.CheckOperatorBlocks() == 0
+
+
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_contraction_engine_selftest(P, ctx, a_k, b_k):
+    """dmrgx_selftest_gemm: the chain kernel on plain products against a double-double-free host reference computed inside the
+    library from the same seeded operands — all four operand layouts, full and ragged tiles (48 / 32 / 16 wide edges), one
+    segment and a chain of 8."""
+    import ctypes as C
+    L = P.lib()
+    for (M, N, K, nseg) in [(256, 320, 512, 1), (256, 320, 512, 8), (64 * 3 + 48, 64 * 2 + 32, 200, 1), (64 + 16, 64 * 2 + 48, 77, 3), (40, 24, 33, 2)]:
+        ms, err = C.c_double(), C.c_double()
+        rc = L.dmrgx_selftest_gemm(ctx.h, C.c_longlong(M), C.c_longlong(N), C.c_longlong(K), a_k, b_k, nseg, 1, C.byref(ms), C.byref(err))
+        assert rc == 0, L.dmrgx_last_error()
+        assert err.value <= 1e-13 * K * nseg, (M, N, K, nseg, err.value)
 
 
 def test_sparse_and_dense_tile_paths_agree(P, ctx, orc):

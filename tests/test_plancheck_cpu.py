@@ -6,6 +6,8 @@ import os
 import subprocess
 
 import numpy as np
+
+import libswitch
 import pytest
 
 import parity_common as pc
@@ -20,9 +22,9 @@ def P():
     if not os.path.exists(PLANCHECK):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "dmrg.x_b200", "csrc"), "plancheck"])
     P = dmrgx_loader.load_package()
-    P.use_library(PLANCHECK)
+    libswitch.use_library(P, PLANCHECK)
     yield P
-    P.use_library(None)
+    libswitch.use_library(P, None)
 
 
 @pytest.fixture()
@@ -140,7 +142,7 @@ def test_no_device_no_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    lib = C.CDLL(P.LIB_PATH)
+    lib = C.CDLL(os.path.join(ROOT, "dmrg.x_b200", "libdmrgx_b200.so"))   # the PRODUCT library, not the emulation build
     h = C.c_void_p()
     assert lib.dmrgx_ctx_create(0, None, C.byref(h)) == 100
 
@@ -181,3 +183,22 @@ def test_testkron01_kronblocks_golden(P, ctx, golden_dir):
 
 def test_frozen_step_fixture(P, ctx, golden_dir):
     pc.check_step_fixture(P, ctx, golden_dir)
+
+
+def test_argument_validation_at_the_abi(P, ctx):
+    """-H_eps_ncv beyond what the fused Lanczos kernels hold is refused with PETSC_ERR_ARG_OUTOFRANGE (63) and a message,
+    instead of failing mid-solve; CSR row pointers that decrease are refused with PETSC_ERR_ARG_CORRUPT (64)."""
+    import bench_workload as W
+    sw = W.ExactChainWorkload(P, ctx, 4)
+    with pytest.raises(P.DmrgxError) as e:
+        sw.shell.EPSSolve(ncv=40)
+    assert e.value.code == 63 and "ncv" in str(e.value)
+    e0, _, st = sw.shell.EPSSolve(ncv=39, tol=1e-10)
+    assert st["converged"]
+    b = P.Block.Initialize(ctx, 1, [0.5, -0.5], [2, 2])
+    with pytest.raises(P.DmrgxError) as e:
+        b.set_operator(P.OpSz, 0, [0, 3, 1, 2, 2], [0, 1, 0], [1.0, 1.0, 1.0])
+    assert e.value.code == 64
+    with pytest.raises(P.DmrgxError) as e:
+        b.set_operator(P.OpSz, 0, [1, 1, 1, 1, 1], [0], [1.0])
+    assert e.value.code == 64

@@ -7,7 +7,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dmrgx_loader
 
 P = dmrgx_loader.load_package()
-P.use_library(None)
 ctx = P.Context(0)
 L = P.lib()
 for (M, N, K, ak, bk, nseg) in [(4096, 4736, 2048, 1, 1, 1), (4096, 4736, 2048, 1, 0, 1), (4096, 4736, 2048, 0, 0, 1), (4096, 4736, 2048, 0, 1, 1),

@@ -7,7 +7,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dmrgx_loader
 
 P = dmrgx_loader.load_package()
-P.use_library(None)
 ctx = P.Context(0)
 L = P.lib()
 def run(M, N, K, nseg=1, ak=1, bk=1):
