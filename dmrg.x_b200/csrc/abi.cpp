@@ -160,6 +160,7 @@ int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmr
 int dmrgx_hshell_apply_stage(dmrgx_hshell h, int stage, const double* d_x, double* d_y) {
     return guard([&] {
         HShell* s = H(h);
+        if (s->sparse) { if (stage == 2) hshell_apply(s, d_x, d_y); else if (stage != 1) throw Err(ERR_ARG_WRONG, "stage must be 1 or 2"); return; }
         if (stage == 1) s->stage1.run(s->ctx, d_x, nullptr);
         else if (stage == 2) s->stage2.run(s->ctx, d_x, d_y);
         else throw Err(ERR_ARG_WRONG, "stage must be 1 or 2");
@@ -234,7 +235,7 @@ int dmrgx_hshell_stats(dmrgx_hshell h, dmrgx_int* nstates, dmrgx_int* nterms, do
     if (alg_bytes) *alg_bytes = (double)s->alg_bytes;
     if (alg_flops) *alg_flops = s->alg_flops;
     if (nt1) *nt1 = (dmrgx_int)s->stage1.items.size();
-    if (nt2) *nt2 = (dmrgx_int)s->stage2.items.size();
+    if (nt2) *nt2 = s->sparse ? (dmrgx_int)s->sparse->tiles.size() : (dmrgx_int)s->stage2.items.size();
     return 0;
 }
 

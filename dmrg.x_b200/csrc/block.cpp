@@ -221,11 +221,14 @@ static void commit_packer(Ctx* ctx, Packer& pk, std::vector<Tile>* out_flat, Ope
         bv = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, pk.val.size()) * 8); dev::h2d(ctx->st, bv->p, pk.val.data(), pk.val.size() * 8);
     }
     dev::sync(ctx->st);
+    std::shared_ptr<HostCsr> host;
+    if (!pk.rowptr.empty()) { host = std::make_shared<HostCsr>(); host->rowptr = pk.rowptr; host->col = pk.col; host->val = pk.val; }
     for (auto& pe : pk.pend) {
         Tile t = pe.t;
         if (t.fmt == T_DENSE) { t.d = bd->as<double>() + pe.dense_off; t.owner = bd; }
         else if (t.fmt == T_CSR) {
             t.rowptr = br->as<int>() + pe.rp_off; t.col = bc->as<int>() + pe.ci_off; t.val = bv->as<double>() + pe.ci_off;
+            t.hcsr = host; t.h_rp = (long long)pe.rp_off; t.h_ci = (long long)pe.ci_off;
             /* one owner keeps all three arrays alive */
             struct Triple : DevBuf { BufRef a, b, c; Triple(Ctx* c0) : DevBuf(c0, 8) {} };
             auto tr = std::make_shared<Triple>(ctx); tr->a = br; tr->b = bc; tr->c = bv;

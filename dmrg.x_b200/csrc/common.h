@@ -64,6 +64,10 @@ struct Sectors {
 
 enum TileFmt : int { T_DENSE = 0, T_CSR = 1, T_EYE = 2 };
 
+/* host copy of the packed CSR arrays of one uploaded operator (small: exact, un-truncated blocks only) — the sparse
+   shell planner flattens them per sector without reading them back from the device */
+struct HostCsr { std::vector<int> rowptr, col; std::vector<double> val; };
+
 /* A rectangular piece of one sector block (I, I+shift) of an operator, in GLOBAL block coordinates. */
 struct Tile {
     int r0 = 0, c0 = 0, nr = 0, nc = 0;
@@ -76,6 +80,8 @@ struct Tile {
     const int* col = nullptr;
     const double* val = nullptr;
     long long nnz = 0;
+    std::shared_ptr<const HostCsr> hcsr; /* CSR: row i of this tile = entries [hcsr->rowptr[h_rp+i], hcsr->rowptr[h_rp+i+1]) of */
+    long long h_rp = 0, h_ci = 0;        /*      hcsr->col / val starting at h_ci (the same numbers the device arrays hold)   */
     /* EYE: scale * I_nr */
     double scale = 1.0;
     BufRef owner;
@@ -131,6 +137,17 @@ struct Plan {
     double exec_flops = 0; /* what the kernel executes for them: padded to whole fragments and K chunks */
 };
 
+/* The sparse-sector form of the shell (north_star (a): un-truncated blocks whose operators are CSR / scaled-identity
+   tiles): ONE fused launch of spmm_kernel per apply instead of the two chain launches. */
+struct SparsePlan {
+    std::vector<dev::SpTile> tiles;
+    std::vector<dev::SpPair> pairs;
+    std::vector<dev::SpTerm> terms;
+    BufRef d_tiles, d_pairs, d_terms, d_int, d_val;
+    int max_nR = 0;
+    double flops = 0;
+};
+
 struct HShell {
     Ctx* ctx = nullptr;
     const Kron* kron = nullptr;
@@ -139,6 +156,7 @@ struct HShell {
     long long row_begin = 0, row_end = 0;
     std::vector<long long> row_cuts;
     Plan stage1, stage2;
+    std::unique_ptr<SparsePlan> sparse; /* when set, the apply is one spmm launch and stage1 / stage2 are empty */
     BufRef work;                 /* V panels of stage 1 */
     BufRef xbuf, ybuf;           /* device staging of the host-buffer entry point */
     void* h_pinned = nullptr;

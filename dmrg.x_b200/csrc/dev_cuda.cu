@@ -85,6 +85,7 @@ struct Stream {
     std::vector<cudaEvent_t> ev_lane;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    int spmm_smem = 0;           /* dynamic shared memory spmm_kernel has been configured for on this device */
 };
 constexpr int SOLVER_LANES = 16;
 
@@ -525,6 +526,166 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
 void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y, double* w) {
     if (nitems <= 0) return;
     chain_kernel<<<nitems, NTHREADS, 0, st->s>>>(d_items, d_segs, x, y, w);
+    LAUNCH_CHECK();
+}
+
+/* ================================================================================================
+ *  spmm_kernel — the sparse-sector matvec (north_star (a)): un-truncated blocks, every operator factor a CSR matrix or
+ *  the identity.  One CTA per (sector pair, SP_ROWS consecutive left rows); threads run along the right index, so every
+ *  global access to psi is a coalesced row segment.
+ *    - the CTA's own rows of X_p (one contiguous range of psi) are staged in shared memory by ONE TMA bulk copy
+ *      (cp.async.bulk + mbarrier; a leading / trailing element is patched by hand when the range is not 16-byte aligned);
+ *      every right-factor gather X[l, col(f)] (1⊗H_R, Sz⊗Sz, ...) and every left-factor entry that falls inside the tile
+ *      (the diagonal and the short-range part of H_L) is then served from shared memory;
+ *    - left-factor entries outside the tile read whole rows of X_q from L2 (psi fits in L2: DRAM sees it once);
+ *    - the CSR entries of the tile's left rows are preloaded into shared memory once per term; the right factor's row of
+ *      output column c is read once per thread and reused for all SP_ROWS rows;
+ *    - all terms of the pair accumulate in registers, y is written exactly once, one launch per apply.
+ * ============================================================================================== */
+constexpr int SP_BD = 256, SP_CH = 4, SP_E = 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__(SP_BD) spmm_kernel(const SpTile* __restrict__ tiles, const SpPair* __restrict__ pairs, const SpTerm* __restrict__ terms,
+                                                    const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ unsigned long long mbar;
+    __shared__ int sa_s[SP_ROWS][SP_E];
+    __shared__ double sa_w[SP_ROWS][SP_E];
+    __shared__ int sa_n[SP_ROWS];
+    __shared__ int sa_more;
+    const SpTile tl = tiles[blockIdx.x];
+    const SpPair P = pairs[tl.pair];
+    const int tid = threadIdx.x, nR = P.nR, nrows = tl.nrows, l0 = tl.l0;
+    /* ---- stage the tile's own rows: nrows*nR contiguous doubles of psi ---- */
+    const double* src = x + P.off + (long long)l0 * nR;
+    const int cnt = nrows * nR;
+    const int head = (int)(((unsigned long long)src >> 3) & 1ull);   /* 1: src is 8 mod 16 */
+    double* xs = (double*)sp_smem + head;                              /* xs + head is 16-byte aligned */
+    const int bulk = (cnt - head) & ~1;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0 && bulk > 0) {
+        mbar_expect_tx(&mbar, (unsigned)bulk * 8u);
+        bulk_g2s(xs + head, src + head, (unsigned)bulk * 8u, &mbar);
+    }
+    if (tid == 32 && head) xs[0] = src[0];
+    if (tid == 64 && head + bulk < cnt) xs[cnt - 1] = src[cnt - 1];
+    if (bulk > 0) mbar_wait(&mbar, 0);
+    __syncthreads();
+
+    for (int cb0 = 0; cb0 < nR; cb0 += SP_CH * SP_BD) {
+        double acc[SP_CH][SP_ROWS];
+#pragma unroll
+        for (int j = 0; j < SP_CH; ++j)
+#pragma unroll
+            for (int r = 0; r < SP_ROWS; ++r) acc[j][r] = 0.0;
+        for (int t = P.term_begin; t < P.term_end; ++t) {
+            const SpTerm T = terms[t];
+            const double* xq = x + T.xoff;
+            for (int ebase = 0;; ebase += SP_E) {
+                __syncthreads(); /* the previous batch has been consumed */
+                if (tid < SP_ROWS * SP_E) {
+                    const int r = tid / SP_E, k = tid % SP_E;
+                    if (r < nrows) {
+                        const int e = T.a_rowptr[l0 + r] + ebase + k;
+                        if (e < T.a_rowptr[l0 + r + 1]) { sa_s[r][k] = T.a_col[e]; sa_w[r][k] = T.coef * T.a_val[e]; }
+                    }
+                }
+                if (tid == 0) {
+                    int more = 0;
+                    for (int r = 0; r < SP_ROWS; ++r) {
+                        int len = r < nrows ? T.a_rowptr[l0 + r + 1] - T.a_rowptr[l0 + r] - ebase : 0;
+                        if (len > SP_E) { more = 1; len = SP_E; }
+                        sa_n[r] = len < 0 ? 0 : len;
+                    }
+                    sa_more = more;
+                }
+                __syncthreads();
+                if (!T.b_rowptr) {
+                    /* identity on the right: acc(r, c) += w · X_q(s, c) */
+#pragma unroll
+                    for (int r = 0; r < SP_ROWS; ++r) {
+                        const int n = sa_n[r];
+                        for (int k = 0; k < n; ++k) {
+                            const int sr = sa_s[r][k];
+                            const double w = sa_w[r][k];
+                            if (T.self && sr >= l0 && sr < l0 + nrows) {
+                                const double* p = xs + (sr - l0) * nR + cb0 + tid;
+#pragma unroll
+                                for (int j = 0; j < SP_CH; ++j)
+                                    if (cb0 + tid + j * SP_BD < nR) acc[j][r] += w * p[j * SP_BD];
+                            } else {
+                                const double* p = xq + (long long)sr * T.nRq + cb0 + tid;
+#pragma unroll
+                                for (int j = 0; j < SP_CH; ++j)
+                                    if (cb0 + tid + j * SP_BD < nR) acc[j][r] += w * __ldg(p + j * SP_BD);
+                            }
+                        }
+                    }
+                } else {
+                    /* CSR on the right: acc(r, c) += w · Σ_f B(c, f) · X_q(s, col_f); the row of B is read once per column */
+#pragma unroll
+                    for (int j = 0; j < SP_CH; ++j) {
+                        const int c = cb0 + tid + j * SP_BD;
+                        if (c >= nR) continue;
+                        const int f1 = T.b_rowptr[c + 1];
+                        for (int f = T.b_rowptr[c]; f < f1; ++f) {
+                            const int cf = T.b_col[f];
+                            const double vb = T.b_val[f];
+#pragma unroll
+                            for (int r = 0; r < SP_ROWS; ++r) {
+                                const int n = sa_n[r];
+                                for (int k = 0; k < n; ++k) {
+                                    const int sr = sa_s[r][k];
+                                    const double xv = (T.self && sr >= l0 && sr < l0 + nrows) ? xs[(sr - l0) * nR + cf] : __ldg(xq + (long long)sr * T.nRq + cf);
+                                    acc[j][r] += sa_w[r][k] * vb * xv;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!sa_more) break;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SP_ROWS; ++r) {
+            if (r >= nrows) continue;
+            double* yr = y + P.off + (long long)(l0 + r) * nR + cb0 + tid;
+#pragma unroll
+            for (int j = 0; j < SP_CH; ++j)
+                if (cb0 + tid + j * SP_BD < nR) yr[j * SP_BD] = acc[j][r];
+        }
+    }
+}
+
+void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpPair* d_pairs, const SpTerm* d_terms, const double* x, double* y, int max_nR) {
+    if (ntiles <= 0) return;
+    if (max_nR > SP_MAX_NR) throw std::runtime_error("run_spmm: right sector too wide for the shared-memory stage");
+    const int smem = SP_ROWS * max_nR * 8 + 32;
+    if (smem > st->spmm_smem) { /* a per-device attribute, raised once per context */
+        CUDA_OK(cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        st->spmm_smem = smem;
+    }
+    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_pairs, d_terms, x, y);
     LAUNCH_CHECK();
 }
 

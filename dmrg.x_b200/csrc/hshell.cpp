@@ -73,9 +73,168 @@ static bool clip_tile_rows(Tile& t, int lo, int hi) {
     if (b <= a) return false;
     const int d = a - t.r0;
     if (t.fmt == T_DENSE) t.d += (long long)d * t.sr;
-    else if (t.fmt == T_CSR) t.rowptr += d;   /* row pointers are absolute offsets into col/val */
+    else if (t.fmt == T_CSR) { t.rowptr += d; t.h_rp += d; }   /* row pointers are absolute offsets into col/val */
     else { t.c0 += d; t.nc = b - a; }          /* a run of a scaled identity */
     t.r0 = a; t.nr = b - a;
+    return true;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ *  Sparse-sector shell (north_star (a)).  When every operator tile the terms touch is CSR or a scaled identity — exact,
+ *  un-truncated blocks handed over as CSR — the two-stage dense plan is replaced by one fused SpMM launch: per sector pair
+ *  the terms Σ_t coef_t · A_t · X_q · B_tᵀ are evaluated row by row straight from ψ, with no V workspace at all
+ *  (the reference's inner loop for these rows is src/DMRGKron.cpp:1844-1864).  The per-sector CSR of every factor is
+ *  flattened on the host from the tiles' host copies (EYE runs become explicit entries) and uploaded once.
+ * ---------------------------------------------------------------------------------------------- */
+namespace {
+struct FlatCsr { std::vector<int> rowptr, col; std::vector<double> val; long long ioff = 0, voff = 0; };
+
+/* rows of sector I of operator O (columns local to sector J) as CSR; false when a tile is dense (or has no host copy) */
+bool flatten_sector(const Operator* O, const Sectors& S, int I, int J, FlatCsr& out) {
+    const int nI = S.size[I];
+    std::vector<std::vector<std::pair<int, double>>> rows(nI);
+    for (const Tile& t : O->tiles[I]) {
+        const int r0 = t.r0 - S.off[I], c0 = t.c0 - S.off[J];
+        if (t.fmt == T_DENSE) return false;
+        if (t.fmt == T_EYE) {
+            for (int i = 0; i < t.nr; ++i) rows[r0 + i].push_back({c0 + i, t.scale});
+        } else {
+            if (!t.hcsr) return false;
+            const HostCsr& h = *t.hcsr;
+            for (int i = 0; i < t.nr; ++i)
+                for (int e = h.rowptr[t.h_rp + i]; e < h.rowptr[t.h_rp + i + 1]; ++e) rows[r0 + i].push_back({c0 + h.col[t.h_ci + e], h.val[t.h_ci + e]});
+        }
+    }
+    out.rowptr.assign(nI + 1, 0);
+    for (int i = 0; i < nI; ++i) {
+        auto& r = rows[i];
+        std::sort(r.begin(), r.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+        for (size_t k = 0; k < r.size(); ++k) {
+            if (k > 0 && r[k].first == out.col.back() && (int)out.col.size() > out.rowptr[i]) out.val.back() += r[k].second;
+            else { out.col.push_back(r[k].first); out.val.push_back(r[k].second); }
+        }
+        out.rowptr[i + 1] = (int)out.col.size();
+    }
+    return true;
+}
+}  // namespace
+
+/* Returns false (and leaves H untouched) when the superblock is not purely sparse. */
+static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Group>& groups, const std::vector<int>& lr0, const std::vector<int>& lr1,
+                             long long& tile_bytes, bool dry) {
+    if (getenv("DMRGX_NO_SPARSE")) return false; /* experiment / test hook: force the chain-kernel path */
+    Ctx* ctx = kron->ctx;
+    const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
+    const int np = (int)kron->pairs.size();
+    for (const Group& G : groups) {
+        if (G.A) for (const auto& v : G.A->tiles) for (const Tile& t : v) if (t.fmt == T_DENSE || (t.fmt == T_CSR && !t.hcsr)) return false;
+        for (const RightFactor& rf : G.rights)
+            if (rf.B) for (const auto& v : rf.B->tiles) for (const Tile& t : v) if (t.fmt == T_DENSE || (t.fmt == T_CSR && !t.hcsr)) return false;
+    }
+    for (int p = 0; p < np; ++p) if (SR.size[kron->pairs[p].ir] > dev::SP_MAX_NR) return false;
+
+    std::unique_ptr<SparsePlan> sp(new SparsePlan());
+    std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>> cacheL, cacheR;
+    std::vector<std::shared_ptr<FlatCsr>> all; /* upload order */
+    std::shared_ptr<FlatCsr> eyeL_dummy;
+    std::map<int, std::shared_ptr<FlatCsr>> eyeL; /* identity on a left sector */
+    auto get = [&](std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>>& cache, const Operator* O, const Sectors& S, int I, int J) {
+        auto key = std::make_pair(O, I);
+        auto f = cache.find(key);
+        if (f != cache.end()) return f->second;
+        auto fc = std::make_shared<FlatCsr>();
+        if (!flatten_sector(O, S, I, J, *fc)) throw Err(ERR_GENERIC, "sparse shell: unexpected dense tile");
+        cache[key] = fc; all.push_back(fc);
+        return fc;
+    };
+    auto get_eye = [&](int I) {
+        auto f = eyeL.find(I);
+        if (f != eyeL.end()) return f->second;
+        auto fc = std::make_shared<FlatCsr>();
+        const int n = SL.size[I];
+        fc->rowptr.resize(n + 1);
+        for (int i = 0; i <= n; ++i) fc->rowptr[i] = i;
+        for (int i = 0; i < n; ++i) { fc->col.push_back(i); fc->val.push_back(1.0); }
+        eyeL[I] = fc; all.push_back(fc);
+        return fc;
+    };
+    std::set<const void*> touched;
+    auto touch = [&](const Tile& t) {
+        const void* key = t.fmt == T_CSR ? (const void*)t.val : nullptr;
+        if (key && touched.insert(key).second) tile_bytes += t.bytes();
+    };
+    struct PendingTerm { std::shared_ptr<FlatCsr> a, b; dev::SpTerm t; };
+    std::vector<PendingTerm> pend;
+    for (int p = 0; p < np; ++p) {
+        const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
+        const int nL = SL.size[il], nR = SR.size[ir];
+        dev::SpPair P;
+        std::memset(&P, 0, sizeof P);
+        P.off = kron->off[p]; P.nL = nL; P.nR = nR; P.term_begin = (int)pend.size();
+        if (lr1[p] > lr0[p] && nR > 0) {
+            for (const Group& G : groups) {
+                const int jl = il + G.sA, jr = ir + G.sB;
+                if (jl < 0 || jl >= SL.nsec() || jr < 0 || jr >= SR.nsec()) continue;
+                const int q = kron->find(jl, jr);
+                if (q < 0 || SL.size[jl] == 0 || SR.size[jr] == 0) continue;
+                std::shared_ptr<FlatCsr> a = G.A ? get(cacheL, G.A, SL, il, jl) : get_eye(il);
+                if (G.A) for (const Tile& t : G.A->tiles[il]) touch(t);
+                long long annz = a->rowptr[lr1[p]] - a->rowptr[lr0[p]];
+                if (annz == 0) continue;
+                for (const RightFactor& rf : G.rights) {
+                    std::shared_ptr<FlatCsr> b;
+                    if (rf.B) {
+                        b = get(cacheR, rf.B, SR, ir, jr);
+                        for (const Tile& t : rf.B->tiles[ir]) touch(t);
+                        if (b->col.empty()) continue;
+                    }
+                    PendingTerm pt;
+                    pt.a = a; pt.b = b;
+                    std::memset(&pt.t, 0, sizeof pt.t);
+                    pt.t.xoff = kron->off[q]; pt.t.coef = rf.coef; pt.t.nRq = SR.size[jr]; pt.t.self = (q == p) ? 1 : 0;
+                    pend.push_back(pt);
+                    sp->flops += b ? 2.0 * (double)annz * (double)b->col.size() : 2.0 * (double)annz * nR;
+                }
+            }
+        }
+        P.term_end = (int)pend.size();
+        sp->pairs.push_back(P);
+        if (P.term_end > P.term_begin || lr1[p] > lr0[p])
+            for (int l0 = lr0[p]; l0 < lr1[p]; l0 += dev::SP_ROWS) sp->tiles.push_back({p, l0, std::min(dev::SP_ROWS, lr1[p] - l0), 0});
+        sp->max_nR = std::max(sp->max_nR, nR);
+    }
+    /* widest rows first: the hardware dispatches CTAs in index order (LPT) */
+    std::stable_sort(sp->tiles.begin(), sp->tiles.end(), [&](const dev::SpTile& a, const dev::SpTile& b) { return sp->pairs[a.pair].nR > sp->pairs[b.pair].nR; });
+    if (!dry) {
+        long long ni = 0, nv = 0;
+        for (auto& fc : all) { fc->ioff = ni; ni += (long long)fc->rowptr.size() + (long long)fc->col.size(); fc->voff = nv; nv += (long long)fc->val.size(); }
+        std::vector<int> hi((size_t)std::max<long long>(1, ni));
+        std::vector<double> hv((size_t)std::max<long long>(1, nv));
+        for (auto& fc : all) {
+            std::copy(fc->rowptr.begin(), fc->rowptr.end(), hi.begin() + fc->ioff);
+            std::copy(fc->col.begin(), fc->col.end(), hi.begin() + fc->ioff + (long long)fc->rowptr.size());
+            std::copy(fc->val.begin(), fc->val.end(), hv.begin() + fc->voff);
+        }
+        sp->d_int = std::make_shared<DevBuf>(ctx, hi.size() * 4);
+        sp->d_val = std::make_shared<DevBuf>(ctx, hv.size() * 8);
+        dev::h2d(ctx->st, sp->d_int->p, hi.data(), hi.size() * 4);
+        dev::h2d(ctx->st, sp->d_val->p, hv.data(), hv.size() * 8);
+        const int* di = sp->d_int->as<int>();
+        const double* dv = sp->d_val->as<double>();
+        for (PendingTerm& pt : pend) {
+            pt.t.a_rowptr = di + pt.a->ioff; pt.t.a_col = pt.t.a_rowptr + pt.a->rowptr.size(); pt.t.a_val = dv + pt.a->voff;
+            if (pt.b) { pt.t.b_rowptr = di + pt.b->ioff; pt.t.b_col = pt.t.b_rowptr + pt.b->rowptr.size(); pt.t.b_val = dv + pt.b->voff; }
+            sp->terms.push_back(pt.t);
+        }
+        sp->d_tiles = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->tiles.size()) * sizeof(dev::SpTile));
+        sp->d_pairs = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->pairs.size()) * sizeof(dev::SpPair));
+        sp->d_terms = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->terms.size()) * sizeof(dev::SpTerm));
+        dev::h2d(ctx->st, sp->d_tiles->p, sp->tiles.data(), sp->tiles.size() * sizeof(dev::SpTile));
+        dev::h2d(ctx->st, sp->d_pairs->p, sp->pairs.data(), sp->pairs.size() * sizeof(dev::SpPair));
+        dev::h2d(ctx->st, sp->d_terms->p, sp->terms.data(), sp->terms.size() * sizeof(dev::SpTerm));
+        dev::sync(ctx->st);
+    }
+    H->sparse = std::move(sp);
     return true;
 }
 
@@ -111,6 +270,18 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
         const void* key = t.fmt == T_DENSE ? (const void*)t.d : (t.fmt == T_CSR ? (const void*)t.val : nullptr);
         if (key && touched.insert(key).second) tile_bytes += t.bytes();
     };
+
+    /* ---- purely sparse superblock (exact blocks handed over as CSR): one fused SpMM launch instead of the two-stage plan ---- */
+    if (try_build_sparse(H.get(), kron, groups, lr0, lr1, tile_bytes, dry)) {
+        if (pair_cost) {
+            const SparsePlan& sp = *H->sparse;
+            for (int p = 0; p < np; ++p) (*pair_cost)[p] = (double)(lr1[p] - lr0[p]) * SR.size[kron->pairs[p].ir] * (sp.pairs[p].term_end - sp.pairs[p].term_begin);
+        }
+        H->alg_bytes = 16LL * H->n + tile_bytes;
+        H->alg_flops = H->sparse->flops;
+        tr.mark("sparse plan");
+        return H.release();
+    }
 
     /* ---- pass 1: size the V workspace ---- */
     struct GP { long long voff; int q; };
@@ -476,6 +647,12 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
 
 /* MatMult_KronSumShell, src/DMRGKron.cpp:1827-1869 */
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
+    if (H->sparse) {
+        const SparsePlan& sp = *H->sparse;
+        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_pairs->as<dev::SpPair>(), sp.d_terms->as<dev::SpTerm>(), d_x, d_y,
+                      sp.max_nR);
+        return;
+    }
     H->stage1.run(H->ctx, d_x, nullptr);
     H->stage2.run(H->ctx, d_x, d_y);
 }

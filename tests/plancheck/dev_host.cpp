@@ -86,6 +86,30 @@ void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, 
     }
 }
 
+void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpPair* pairs, const SpTerm* terms, const double* x, double* y, int) {
+    ++g_launches;
+    for (int w = 0; w < ntiles; ++w) {
+        const SpTile& tl = tiles[w];
+        const SpPair& P = pairs[tl.pair];
+        for (int r = 0; r < tl.nrows; ++r) {
+            const int l = tl.l0 + r;
+            for (int c = 0; c < P.nR; ++c) {
+                double acc = 0.0;
+                for (int t = P.term_begin; t < P.term_end; ++t) {
+                    const SpTerm& T = terms[t];
+                    for (int e = T.a_rowptr[l]; e < T.a_rowptr[l + 1]; ++e) {
+                        const double* row = x + T.xoff + (long long)T.a_col[e] * T.nRq;
+                        const double wgt = T.coef * T.a_val[e];
+                        if (!T.b_rowptr) acc += wgt * row[c];
+                        else for (int f = T.b_rowptr[c]; f < T.b_rowptr[c + 1]; ++f) acc += wgt * T.b_val[f] * row[T.b_col[f]];
+                    }
+                }
+                y[P.off + (long long)l * P.nR + c] = acc;
+            }
+        }
+    }
+}
+
 void run_reduce(Stream*, const ReduceItem* items, int nitems, double* ybase, const double* wbase) {
     ++g_launches;
     for (int i = 0; i < nitems; ++i) {

@@ -42,16 +42,20 @@ def test_restart_and_initialize_from_disk_on_the_device(tmp_path):
     s1 = str(tmp_path) + "/s/"
     r = subprocess.run([EXE] + ham + ["-mwarmup", "24", "-msweeps", "32", "-scratch_dir", s1, "-data_dir", str(tmp_path) + "/d1/"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-1500:]
-    r2 = subprocess.run([EXE, "-restart_dir", s1, "-msweeps", "48", "-H_eps_tol", "1e-12", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d2/"],
+    # (kept-state counts inside degenerate +q / -q multiplets may differ between the two runs — SURVEY.md §7 — so the schedule
+    # columns and the energies are compared, not the sector bookkeeping)
+    r2 = subprocess.run([EXE, "-restart_dir", s1, "-msweeps", "256", "-H_eps_tol", "1e-12", "-do_correlators", "0", "-data_dir", str(tmp_path) + "/d2/"],
                         capture_output=True, text=True)
     assert r2.returncode == 0 and "Loading blocks from file" in r2.stdout, r2.stdout[-1500:] + r2.stderr[-1500:]
-    r3 = subprocess.run([EXE] + ham + ["-mwarmup", "24", "-msweeps", "32,48", "-data_dir", str(tmp_path) + "/d3/"], capture_output=True, text=True)
+    r3 = subprocess.run([EXE] + ham + ["-mwarmup", "24", "-msweeps", "32,256", "-data_dir", str(tmp_path) + "/d3/"], capture_output=True, text=True)
     assert r3.returncode == 0
     t2 = json.load(open(str(tmp_path) + "/d2/DMRGSteps.json"))["table"]
     t3 = json.load(open(str(tmp_path) + "/d3/DMRGSteps.json"))["table"]
     assert len(t2) == 12
     for a, b in zip(t2, t3[-12:]):
-        assert a[:15] == b[:15] and abs(a[-1] - b[-1]) <= 1e-10 * abs(b[-1])
+        assert a[:8] == b[:8] and abs(a[-1] - b[-1]) <= 1e-8 * abs(b[-1]), (a, b)
+    mid = [r for r in t2 if r[4] == r[5]]
+    assert mid and abs(mid[-1][-1] - (-8.261232563030)) < 1e-7        # exact diagonalisation
     # InitializeFromDisk -> enlarge -> superblock -> ground state == the energy of that step in the driver's table
     P = dmrgx_loader.load_package()
     ctx = P.Context(0)

@@ -164,6 +164,66 @@ def test_contraction_engine_selftest(P, ctx, a_k, b_k):
         assert err.value <= 1e-13 * K * nseg, (M, N, K, nseg, err.value)
 
 
+def _oracle_exact_chain(orc, nhalf):
+    """the oracle's own exact halves of the open Heisenberg chain (same enlargement sequence as ExactChainWorkload)"""
+    T = lambda n: orc.ham_terms(2 * nhalf, 1, 0.5, 1.0, 0.0, 0.0, n, 0, 0)
+    site = orc.Block.single_site()
+    blk = orc.Block.single_site()
+    for n in range(2, nhalf + 1):
+        blk = orc.kron_eye(blk, site, T(n))
+    return blk, orc.KronBlocks(blk, blk, [0.0]), T(2 * nhalf)
+
+
+@pytest.mark.parametrize("nhalf", [9, 12, 13])
+def test_sparse_sector_kernel_matches_oracle_and_chain_kernel(P, ctx, orc, nhalf, monkeypatch):
+    """spmm_kernel (the sparse-sector matvec of un-truncated blocks) against (a) the oracle's restatement of
+    MatMult_KronSumShell on row windows and (b) the chain kernel's sparse segments on the whole vector (two independent
+    kernels).  nhalf = 12 is the benchmark's workload (right sectors up to 924 wide: four column chunks per thread);
+    nhalf = 13 has right sectors 1716 wide (two passes of the column super-chunk loop)."""
+    import bench_workload as W
+    sw = W.ExactChainWorkload(P, ctx, nhalf)
+    st = sw.shell.stats()
+    assert st["tiles_stage1"] == 0 and st["tiles_stage2"] > 0          # the sparse plan is in use
+    l0 = P.launch_count()
+    x = sw.random_state(3)
+    y = sw.shell.MatMult_host(x)
+    assert P.launch_count() - l0 == 1                                   # one launch per apply
+    oblk, okb, terms = _oracle_exact_chain(orc, nhalf)
+    pc.check_kron_bookkeeping(P, orc, sw.kron, okb)
+    n = sw.n
+    scale = np.abs(y).max()
+    _, _, _, _, off = sw.kron.data()
+    big = int(np.argmax(np.diff(off)))
+    for c in (0, int(off[big]), int(off[big]) + int(np.diff(off)[big]) // 2, int(off[big + 1]), n):
+        r0, r1 = max(0, c - 1500), min(n, c + 1500)
+        y_ref = orc.Shell(okb, terms, rows=(r0, r1)).apply(x, 4)
+        assert np.abs(y[r0:r1] - y_ref).max() <= 1e-13 * scale * 5
+    monkeypatch.setenv("DMRGX_NO_SPARSE", "1")
+    dense_path = sw.kron.KronSumConstruct(sw.terms)
+    monkeypatch.delenv("DMRGX_NO_SPARSE")
+    assert dense_path.stats()["tiles_stage2"] > 0 and dense_path.stats()["tiles_stage1"] > 0
+    y2 = dense_path.MatMult_host(x)
+    assert np.abs(y - y2).max() <= 1e-13 * scale * 5
+
+
+@pytest.mark.parametrize("config,m", [("j1j2_12x6", 96), ("heis_8x4", 128), ("xy_16x8", 72)])
+def test_sparse_sector_kernel_general_csr_factors(P, ctx, orc, config, m):
+    """the same kernel with BOTH factors of the L-R terms general CSR matrices and rows longer than one preload batch:
+    sector-dense synthetic blocks uploaded with the dense threshold above 1, so every tile is stored as CSR."""
+    import bench_workload as W
+    wl = W.Workload(P, ctx, config, m=m)
+    enl_o, kb_o = W.oracle_side(orc, wl)
+    try:
+        ctx.set_dense_threshold(2.0)
+        up = pc.upload_block(P, ctx, enl_o, orc)      # the ENLARGED block handed over as CSR (route B of INTEGRATION.md)
+    finally:
+        ctx.set_dense_threshold(0.125)
+    shell = P.KronBlocks(up, up, [0.0]).KronSumConstruct(wl.terms)
+    st = shell.stats()
+    assert st["tiles_stage1"] == 0 and st["tiles_stage2"] > 0          # the sparse plan is in use
+    pc.check_matvec(P, orc, ctx, shell, orc.Shell(kb_o, wl.terms), np.random.default_rng(3), nvec=1)
+
+
 def test_sparse_and_dense_tile_paths_agree(P, ctx, orc):
     rng = np.random.default_rng(11)
     ham = J1J2_CYL
