@@ -225,7 +225,13 @@ static void commit_packer(Ctx* ctx, Packer& pk, std::vector<Tile>* out_flat, Ope
     if (!pk.rowptr.empty()) { host = std::make_shared<HostCsr>(); host->rowptr = pk.rowptr; host->col = pk.col; host->val = pk.val; }
     for (auto& pe : pk.pend) {
         Tile t = pe.t;
-        if (t.fmt == T_DENSE) { t.d = bd->as<double>() + pe.dense_off; t.owner = bd; }
+        if (t.fmt == T_DENSE) {
+            t.d = bd->as<double>() + pe.dense_off; t.owner = bd;
+            if ((long long)t.nr * t.nc <= 65536) {
+                t.hdense = std::make_shared<std::vector<double>>(pk.dense.begin() + pe.dense_off, pk.dense.begin() + pe.dense_off + (size_t)t.nr * t.nc);
+                t.h_d0 = 0;
+            }
+        }
         else if (t.fmt == T_CSR) {
             t.rowptr = br->as<int>() + pe.rp_off; t.col = bc->as<int>() + pe.ci_off; t.val = bv->as<double>() + pe.ci_off;
             t.hcsr = host; t.h_rp = (long long)pe.rp_off; t.h_ci = (long long)pe.ci_off;

@@ -82,6 +82,10 @@ struct Tile {
     long long nnz = 0;
     std::shared_ptr<const HostCsr> hcsr; /* CSR: row i of this tile = entries [hcsr->rowptr[h_rp+i], hcsr->rowptr[h_rp+i+1]) of */
     long long h_rp = 0, h_ci = 0;        /*      hcsr->col / val starting at h_ci (the same numbers the device arrays hold)   */
+    /* DENSE tiles of at most 256x256 that came from the host keep a host copy too (the small, filled sector blocks at the edge
+       of an otherwise sparse exact block): element (i,j) = (*hdense)[h_d0 + i*sr + j*sc] */
+    std::shared_ptr<const std::vector<double>> hdense;
+    long long h_d0 = 0;
     /* EYE: scale * I_nr */
     double scale = 1.0;
     BufRef owner;

@@ -72,7 +72,7 @@ static bool clip_tile_rows(Tile& t, int lo, int hi) {
     const int a = std::max(lo, t.r0), b = std::min(hi, t.r0 + t.nr);
     if (b <= a) return false;
     const int d = a - t.r0;
-    if (t.fmt == T_DENSE) t.d += (long long)d * t.sr;
+    if (t.fmt == T_DENSE) { t.d += (long long)d * t.sr; t.h_d0 += (long long)d * t.sr; }
     else if (t.fmt == T_CSR) { t.rowptr += d; t.h_rp += d; }   /* row pointers are absolute offsets into col/val */
     else { t.c0 += d; t.nc = b - a; }          /* a run of a scaled identity */
     t.r0 = a; t.nr = b - a;
@@ -89,14 +89,21 @@ static bool clip_tile_rows(Tile& t, int lo, int hi) {
 namespace {
 struct FlatCsr { std::vector<int> rowptr, col; std::vector<double> val; long long ioff = 0, voff = 0; };
 
-/* rows of sector I of operator O (columns local to sector J) as CSR; false when a tile is dense (or has no host copy) */
+/* rows of sector I of operator O (columns local to sector J) as CSR; false when a tile has no host copy (device-born panels) */
 bool flatten_sector(const Operator* O, const Sectors& S, int I, int J, FlatCsr& out) {
     const int nI = S.size[I];
     std::vector<std::vector<std::pair<int, double>>> rows(nI);
     for (const Tile& t : O->tiles[I]) {
         const int r0 = t.r0 - S.off[I], c0 = t.c0 - S.off[J];
-        if (t.fmt == T_DENSE) return false;
-        if (t.fmt == T_EYE) {
+        if (t.fmt == T_DENSE) {
+            if (!t.hdense) return false;
+            const std::vector<double>& h = *t.hdense;
+            for (int i = 0; i < t.nr; ++i)
+                for (int j = 0; j < t.nc; ++j) {
+                    const double v = h[(size_t)(t.h_d0 + (long long)i * t.sr + (long long)j * t.sc)];
+                    if (v != 0.0) rows[r0 + i].push_back({c0 + j, v});
+                }
+        } else if (t.fmt == T_EYE) {
             for (int i = 0; i < t.nr; ++i) rows[r0 + i].push_back({c0 + i, t.scale});
         } else {
             if (!t.hcsr) return false;
@@ -126,10 +133,24 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
     Ctx* ctx = kron->ctx;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     const int np = (int)kron->pairs.size();
-    for (const Group& G : groups) {
-        if (G.A) for (const auto& v : G.A->tiles) for (const Tile& t : v) if (t.fmt == T_DENSE || (t.fmt == T_CSR && !t.hcsr)) return false;
-        for (const RightFactor& rf : G.rights)
-            if (rf.B) for (const auto& v : rf.B->tiles) for (const Tile& t : v) if (t.fmt == T_DENSE || (t.fmt == T_CSR && !t.hcsr)) return false;
+    /* sparse means: every tile came from the host (CSR, identity runs, or one of the small filled blocks at the edge of an exact
+       block) and the operators are sparse overall — stored non-zeros at most a quarter of the sector-block areas they live in */
+    {
+        double nnz = 0, area = 0;
+        auto scan = [&](const Operator* O) {
+            for (const auto& v : O->tiles)
+                for (const Tile& t : v) {
+                    if ((t.fmt == T_DENSE && !t.hdense) || (t.fmt == T_CSR && !t.hcsr)) return false;
+                    nnz += t.fmt == T_DENSE ? (double)t.nr * t.nc : (t.fmt == T_CSR ? (double)t.nnz : (double)t.nr);
+                    area += (double)t.nr * t.nc;
+                }
+            return true;
+        };
+        for (const Group& G : groups) {
+            if (G.A && !scan(G.A)) return false;
+            for (const RightFactor& rf : G.rights) if (rf.B && !scan(rf.B)) return false;
+        }
+        if (area > 65536.0 && nnz > 0.25 * area) return false;
     }
     for (int p = 0; p < np; ++p) if (SR.size[kron->pairs[p].ir] > dev::SP_MAX_NR) return false;
 
@@ -160,7 +181,7 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
     };
     std::set<const void*> touched;
     auto touch = [&](const Tile& t) {
-        const void* key = t.fmt == T_CSR ? (const void*)t.val : nullptr;
+        const void* key = t.fmt == T_CSR ? (const void*)t.val : (t.fmt == T_DENSE ? (const void*)t.d : nullptr);
         if (key && touched.insert(key).second) tile_bytes += t.bytes();
     };
     struct PendingTerm { std::shared_ptr<FlatCsr> a, b; dev::SpTerm t; };
