@@ -145,9 +145,8 @@ struct Plan {
    tiles): ONE fused launch of spmm_kernel per apply instead of the two chain launches. */
 struct SparsePlan {
     std::vector<dev::SpTile> tiles;
-    std::vector<dev::SpPair> pairs;
-    std::vector<dev::SpTerm> terms;
-    BufRef d_tiles, d_pairs, d_terms, d_int, d_val;
+    std::vector<dev::SpEntry> entries;   /* the row programs, concatenated */
+    BufRef d_tiles, d_entries, d_int, d_val;
     int max_nR = 0;
     double flops = 0;
 };

@@ -99,29 +99,31 @@ void bcast_batch(Stream*, int n, double* const* d_ptr, const long long* count, c
 void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y, double* w = nullptr);
 
 /* ------------------------------------------------------------------------------------------------
- *  Sparse-sector SpMM (north_star (a)): Y_p = Σ_t coef_t · A_t[IL,JL] · X_q(t) · B_t[IR,JR]ᵀ with every factor a CSR matrix
- *  (or the identity), all terms of a sector pair fused: one CTA per (pair, 8 consecutive left rows), the CTA's own rows of
- *  X_p staged in shared memory by one TMA bulk copy, threads along the right index; y written exactly once.
- *  A_t: CSR over the rows of the left sector (column = row of X_q inside its left sector); B_t: CSR over the rows of the
- *  right sector == output columns (column = column of X_q), b_rowptr == nullptr for the identity.
+ *  Sparse-sector SpMM (north_star (a)): Y_p = Σ_t coef_t · A_t[IL,JL] · X_q(t) · B_t[IR,JR]ᵀ with every factor a sparse matrix
+ *  (or the identity), all terms of a sector pair fused: one CTA per (pair, 8 consecutive left rows), one warp per row, lanes
+ *  along the right index; the CTA's own rows of X_p are staged in shared memory by one TMA bulk copy; y is written exactly
+ *  once.  At plan time the terms and the left factors are flattened into a ROW PROGRAM per output row: a short list of
+ *  (source row of psi, weight, right factor) entries, so that a warp reaches its psi loads after two dependent fetches.
  * ---------------------------------------------------------------------------------------------- */
-struct SpTerm {
-    const int* a_rowptr; const int* a_col; const double* a_val;
-    const int* b_rowptr; const int* b_col; const double* b_val;
-    long long xoff;      /* element offset of X_q in x */
-    double coef;
-    int nRq;             /* row length of X_q */
-    int self;            /* X_q is the pair's own block: rows inside the CTA's tile come from shared memory */
+/* One entry of a row program: acc(c) += w · Σ_f B(c, f) · x[src + col_f]   (B == identity when ell_ptr is null: acc(c) += w · x[src + c]).
+   src is the element offset in x of the source row of X_q.  B is stored as sliced ELL over the output columns: slice j holds
+   columns [32j, 32j+32), its W_j = (ell_ptr[j+1] - ell_ptr[j]) / 32 entry slots at ecol / eval[ell_ptr[j] + t*32 + lane] (padding: value 0, column 0). */
+struct SpEntry {
+    long long src;
+    double w;
+    const int* ell_ptr;
+    const int* ecol;
+    const double* eval;
 };
-struct SpPair {
-    long long off;       /* element offset of the pair in x and in y */
-    int nL, nR;
-    int term_begin, term_end;
+constexpr int SP_ROWS = 8;          /* left rows per CTA: one warp per row */
+struct SpTile {
+    long long off;                  /* element offset in x and y of the tile's first row */
+    int nR, nrows;
+    int prog[SP_ROWS + 1];          /* entries of row r: [prog[r], prog[r+1]) of the entry list */
+    int pad[3];
 };
-struct SpTile { int pair, l0, nrows, pad; };
-constexpr int SP_ROWS = 8;          /* left rows per CTA */
 constexpr int SP_MAX_NR = 3072;     /* widest right sector the kernel stages (8 rows x 3072 doubles = 192 KB of shared memory) */
-void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpPair* d_pairs, const SpTerm* d_terms, const double* x, double* y, int max_nR);
+void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpEntry* d_entries, const double* x, double* y, int max_nR);
 
 /* Long accumulation chains are cut into parts that write partial tiles to the w scratch (so that a launch has enough
    equal work items to fill 148 SMs several times over); the parts are then summed in a FIXED order — deterministic,

@@ -530,19 +530,21 @@ void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d
 }
 
 /* ================================================================================================
- *  spmm_kernel — the sparse-sector matvec (north_star (a)): un-truncated blocks, every operator factor a CSR matrix or
- *  the identity.  One CTA per (sector pair, SP_ROWS consecutive left rows); threads run along the right index, so every
- *  global access to psi is a coalesced row segment.
+ *  spmm_kernel — the sparse-sector matvec (north_star (a)): un-truncated blocks, every operator factor sparse or the
+ *  identity.  One CTA per (sector pair, SP_ROWS consecutive left rows), one WARP per output row, lanes along the right
+ *  index, so every access to psi is a coalesced row segment and a lane keeps its 32 (strided) output columns in registers.
  *    - the CTA's own rows of X_p (one contiguous range of psi) are staged in shared memory by ONE TMA bulk copy
  *      (cp.async.bulk + mbarrier; a leading / trailing element is patched by hand when the range is not 16-byte aligned);
  *      every right-factor gather X[l, col(f)] (1⊗H_R, Sz⊗Sz, ...) and every left-factor entry that falls inside the tile
  *      (the diagonal and the short-range part of H_L) is then served from shared memory;
- *    - left-factor entries outside the tile read whole rows of X_q from L2 (psi fits in L2: DRAM sees it once);
- *    - the CSR entries of the tile's left rows are preloaded into shared memory once per term; the right factor's row of
- *      output column c is read once per thread and reused for all SP_ROWS rows;
- *    - all terms of the pair accumulate in registers, y is written exactly once, one launch per apply.
+ *    - left-factor entries outside the tile read whole rows of X_q from L2 (psi fits in L2: DRAM sees it once), 32
+ *      independent coalesced loads per lane in flight;
+ *    - right factors are sliced ELL (32 output columns per slice, column-major inside a slice): coalesced, branch-free reads
+ *      of (column, value) pairs, no row-pointer indirection;
+ *    - the row program (terms x left-factor entries, flattened at plan time) is fetched lane-parallel while the TMA copy
+ *      is in flight; all terms accumulate in registers, y is written exactly once, one launch per apply.
  * ============================================================================================== */
-constexpr int SP_BD = 256, SP_CH = 4, SP_E = 16;
+constexpr int SP_BD = 32 * SP_ROWS, SP_CH = 32;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
@@ -564,120 +566,100 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     } while (!ok);
 }
 
-__global__ void __launch_bounds__(SP_BD) spmm_kernel(const SpTile* __restrict__ tiles, const SpPair* __restrict__ pairs, const SpTerm* __restrict__ terms,
-                                                    const double* __restrict__ x, double* __restrict__ y) {
-    extern __shared__ __align__(16) unsigned char sp_smem[];
-    __shared__ unsigned long long mbar;
-    __shared__ int sa_s[SP_ROWS][SP_E];
-    __shared__ double sa_w[SP_ROWS][SP_E];
-    __shared__ int sa_n[SP_ROWS];
-    __shared__ int sa_more;
-    const SpTile tl = tiles[blockIdx.x];
-    const SpPair P = pairs[tl.pair];
-    const int tid = threadIdx.x, nR = P.nR, nrows = tl.nrows, l0 = tl.l0;
-    /* ---- stage the tile's own rows: nrows*nR contiguous doubles of psi ---- */
-    const double* src = x + P.off + (long long)l0 * nR;
-    const int cnt = nrows * nR;
-    const int head = (int)(((unsigned long long)src >> 3) & 1ull);   /* 1: src is 8 mod 16 */
-    double* xs = (double*)sp_smem + head;                              /* xs + head is 16-byte aligned */
-    const int bulk = (cnt - head) & ~1;
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    if (tid == 0 && bulk > 0) {
-        mbar_expect_tx(&mbar, (unsigned)bulk * 8u);
-        bulk_g2s(xs + head, src + head, (unsigned)bulk * 8u, &mbar);
-    }
-    if (tid == 32 && head) xs[0] = src[0];
-    if (tid == 64 && head + bulk < cnt) xs[cnt - 1] = src[cnt - 1];
-    if (bulk > 0) mbar_wait(&mbar, 0);
-    __syncthreads();
-
-    for (int cb0 = 0; cb0 < nR; cb0 += SP_CH * SP_BD) {
-        double acc[SP_CH][SP_ROWS];
+/* acc(c) += w · p[c] for the lane's columns c = cb0 + lane + 32 j */
+template <bool SMEM>
+__device__ __forceinline__ void sp_axpy(double (&acc)[SP_CH], const double* p, double w, int ncol) {
 #pragma unroll
-        for (int j = 0; j < SP_CH; ++j)
+    for (int h = 0; h < SP_CH; h += 16) { /* 16 independent loads in flight per lane, then their FMAs */
+        double v[16];
 #pragma unroll
-            for (int r = 0; r < SP_ROWS; ++r) acc[j][r] = 0.0;
-        for (int t = P.term_begin; t < P.term_end; ++t) {
-            const SpTerm T = terms[t];
-            const double* xq = x + T.xoff;
-            for (int ebase = 0;; ebase += SP_E) {
-                __syncthreads(); /* the previous batch has been consumed */
-                if (tid < SP_ROWS * SP_E) {
-                    const int r = tid / SP_E, k = tid % SP_E;
-                    if (r < nrows) {
-                        const int e = T.a_rowptr[l0 + r] + ebase + k;
-                        if (e < T.a_rowptr[l0 + r + 1]) { sa_s[r][k] = T.a_col[e]; sa_w[r][k] = T.coef * T.a_val[e]; }
-                    }
-                }
-                if (tid == 0) {
-                    int more = 0;
-                    for (int r = 0; r < SP_ROWS; ++r) {
-                        int len = r < nrows ? T.a_rowptr[l0 + r + 1] - T.a_rowptr[l0 + r] - ebase : 0;
-                        if (len > SP_E) { more = 1; len = SP_E; }
-                        sa_n[r] = len < 0 ? 0 : len;
-                    }
-                    sa_more = more;
-                }
-                __syncthreads();
-                if (!T.b_rowptr) {
-                    /* identity on the right: acc(r, c) += w · X_q(s, c) */
+        for (int j = 0; j < 16; ++j) v[j] = (32 * (h + j) < ncol) ? (SMEM ? p[32 * (h + j)] : __ldg(p + 32 * (h + j))) : 0.0;
 #pragma unroll
-                    for (int r = 0; r < SP_ROWS; ++r) {
-                        const int n = sa_n[r];
-                        for (int k = 0; k < n; ++k) {
-                            const int sr = sa_s[r][k];
-                            const double w = sa_w[r][k];
-                            if (T.self && sr >= l0 && sr < l0 + nrows) {
-                                const double* p = xs + (sr - l0) * nR + cb0 + tid;
-#pragma unroll
-                                for (int j = 0; j < SP_CH; ++j)
-                                    if (cb0 + tid + j * SP_BD < nR) acc[j][r] += w * p[j * SP_BD];
-                            } else {
-                                const double* p = xq + (long long)sr * T.nRq + cb0 + tid;
-#pragma unroll
-                                for (int j = 0; j < SP_CH; ++j)
-                                    if (cb0 + tid + j * SP_BD < nR) acc[j][r] += w * __ldg(p + j * SP_BD);
-                            }
-                        }
-                    }
-                } else {
-                    /* CSR on the right: acc(r, c) += w · Σ_f B(c, f) · X_q(s, col_f); the row of B is read once per column */
-#pragma unroll
-                    for (int j = 0; j < SP_CH; ++j) {
-                        const int c = cb0 + tid + j * SP_BD;
-                        if (c >= nR) continue;
-                        const int f1 = T.b_rowptr[c + 1];
-                        for (int f = T.b_rowptr[c]; f < f1; ++f) {
-                            const int cf = T.b_col[f];
-                            const double vb = T.b_val[f];
-#pragma unroll
-                            for (int r = 0; r < SP_ROWS; ++r) {
-                                const int n = sa_n[r];
-                                for (int k = 0; k < n; ++k) {
-                                    const int sr = sa_s[r][k];
-                                    const double xv = (T.self && sr >= l0 && sr < l0 + nrows) ? xs[(sr - l0) * nR + cf] : __ldg(xq + (long long)sr * T.nRq + cf);
-                                    acc[j][r] += sa_w[r][k] * vb * xv;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (!sa_more) break;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < SP_ROWS; ++r) {
-            if (r >= nrows) continue;
-            double* yr = y + P.off + (long long)(l0 + r) * nR + cb0 + tid;
-#pragma unroll
-            for (int j = 0; j < SP_CH; ++j)
-                if (cb0 + tid + j * SP_BD < nR) yr[j * SP_BD] = acc[j][r];
-        }
+        for (int j = 0; j < 16; ++j) acc[h + j] += w * v[j];
     }
 }
 
-void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpPair* d_pairs, const SpTerm* d_terms, const double* x, double* y, int max_nR) {
+__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpEntry* __restrict__ entries, const double* __restrict__ x,
+                                                       double* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ unsigned long long mbar;
+    __shared__ SpTile s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    if (tid < (int)(sizeof(SpTile) / 4)) ((int*)&s_tile)[tid] = ((const int*)(tiles + blockIdx.x))[tid];
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    const int nR = s_tile.nR, nrows = s_tile.nrows;
+    const long long off0 = s_tile.off;
+    /* ---- stage the tile's own rows: nrows*nR contiguous doubles of psi ---- */
+    const double* src0 = x + off0;
+    const int cnt = nrows * nR;
+    const int head = (int)(((unsigned long long)src0 >> 3) & 1ull);   /* 1: the range starts 8 mod 16 */
+    double* xs = (double*)sp_smem + head;                               /* xs + head is 16-byte aligned */
+    const int bulk = (cnt - head) & ~1;
+    if (tid == 0 && bulk > 0) {
+        mbar_expect_tx(&mbar, (unsigned)bulk * 8u);
+        bulk_g2s(xs + head, src0 + head, (unsigned)bulk * 8u, &mbar);
+    }
+    if (tid == 32 && head) xs[0] = src0[0];
+    if (tid == 64 && head + bulk < cnt) xs[cnt - 1] = src0[cnt - 1];
+    /* ---- this warp's row program, fetched while the copy is in flight ---- */
+    const int e0 = row < nrows ? s_tile.prog[row] : 0, e1 = row < nrows ? s_tile.prog[row + 1] : 0;
+    SpEntry ent;
+    ent.src = 0; ent.w = 0.0; ent.ell_ptr = nullptr; ent.ecol = nullptr; ent.eval = nullptr;
+    if (e0 + lane < e1) ent = entries[e0 + lane];
+    if (bulk > 0) mbar_wait(&mbar, 0);
+    __syncthreads();
+    if (row >= nrows) return;
+    const long long tile_end = off0 + cnt;
+    for (int cb0 = 0; cb0 < nR; cb0 += 32 * SP_CH) {
+        const int ncol = nR - cb0 - lane; /* the lane owns columns cb0 + lane + 32 j while 32 j < ncol */
+        double acc[SP_CH];
+#pragma unroll
+        for (int j = 0; j < SP_CH; ++j) acc[j] = 0.0;
+        for (int eb = e0; eb < e1; eb += 32) {
+            if (eb != e0 || cb0 != 0) { /* a later batch of a long program, or a later column pass */
+                ent.w = 0.0; ent.src = 0; ent.ell_ptr = nullptr;
+                if (eb + lane < e1) ent = entries[eb + lane];
+            }
+            const int nb = min(32, e1 - eb);
+            for (int k = 0; k < nb; ++k) {
+                const long long src = __shfl_sync(0xffffffffu, ent.src, k);
+                const double w = __shfl_sync(0xffffffffu, ent.w, k);
+                const int* ell = (const int*)__shfl_sync(0xffffffffu, (unsigned long long)ent.ell_ptr, k);
+                const bool in_tile = src >= off0 && src < tile_end;
+                if (!ell) {
+                    if (in_tile) sp_axpy<true>(acc, xs + (src - off0) + cb0 + lane, w, ncol);
+                    else sp_axpy<false>(acc, x + src + cb0 + lane, w, ncol);
+                } else {
+                    const int* ecol = (const int*)__shfl_sync(0xffffffffu, (unsigned long long)ent.ecol, k);
+                    const double* eval = (const double*)__shfl_sync(0xffffffffu, (unsigned long long)ent.eval, k);
+                    const double* gx = in_tile ? xs + (src - off0) : x + src;
+                    const int s0 = cb0 >> 5;
+#pragma unroll
+                    for (int j = 0; j < SP_CH; ++j) {
+                        if (32 * j - lane >= ncol) continue; /* whole slice beyond the row (warp-uniform) */
+                        const int b0 = __ldg(ell + s0 + j), b1 = __ldg(ell + s0 + j + 1);
+                        double a = 0.0;
+                        if (in_tile) {
+#pragma unroll 4
+                            for (int q = b0 + lane; q < b1; q += 32) a += __ldg(eval + q) * gx[__ldg(ecol + q)];
+                        } else {
+#pragma unroll 4
+                            for (int q = b0 + lane; q < b1; q += 32) a += __ldg(eval + q) * __ldg(gx + __ldg(ecol + q));
+                        }
+                        acc[j] += w * a;
+                    }
+                }
+            }
+        }
+        double* yr = y + off0 + (long long)row * nR + cb0 + lane;
+#pragma unroll
+        for (int j = 0; j < SP_CH; ++j)
+            if (32 * j < ncol) yr[32 * j] = acc[j];
+    }
+}
+
+void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpEntry* d_entries, const double* x, double* y, int max_nR) {
     if (ntiles <= 0) return;
     if (max_nR > SP_MAX_NR) throw std::runtime_error("run_spmm: right sector too wide for the shared-memory stage");
     const int smem = SP_ROWS * max_nR * 8 + 32;
@@ -685,7 +667,7 @@ void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpPair* d_pai
         CUDA_OK(cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         st->spmm_smem = smem;
     }
-    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_pairs, d_terms, x, y);
+    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_entries, x, y);
     LAUNCH_CHECK();
 }
 

@@ -130,6 +130,7 @@ bool flatten_sector(const Operator* O, const Sectors& S, int I, int J, FlatCsr& 
 static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Group>& groups, const std::vector<int>& lr0, const std::vector<int>& lr1,
                              long long& tile_bytes, bool dry) {
     if (getenv("DMRGX_NO_SPARSE")) return false; /* experiment / test hook: force the chain-kernel path */
+    const bool force = getenv("DMRGX_FORCE_SPARSE") != nullptr; /* test hook: skip the fill criterion (general CSR factors with long rows) */
     Ctx* ctx = kron->ctx;
     const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
     const int np = (int)kron->pairs.size();
@@ -150,91 +151,116 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
             if (G.A && !scan(G.A)) return false;
             for (const RightFactor& rf : G.rights) if (rf.B && !scan(rf.B)) return false;
         }
-        if (area > 65536.0 && nnz > 0.25 * area) return false;
+        if (!force && area > 65536.0 && nnz > 0.25 * area) return false;
     }
     for (int p = 0; p < np; ++p) if (SR.size[kron->pairs[p].ir] > dev::SP_MAX_NR) return false;
 
     std::unique_ptr<SparsePlan> sp(new SparsePlan());
-    std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>> cacheL, cacheR;
-    std::vector<std::shared_ptr<FlatCsr>> all; /* upload order */
-    std::shared_ptr<FlatCsr> eyeL_dummy;
-    std::map<int, std::shared_ptr<FlatCsr>> eyeL; /* identity on a left sector */
-    auto get = [&](std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>>& cache, const Operator* O, const Sectors& S, int I, int J) {
+    /* flattened factors, cached per (operator, sector): left factors stay on the host (they are folded into the row programs),
+       right factors become sliced-ELL device arrays */
+    struct Ell { std::vector<int> ptr, col; std::vector<double> val; long long ioff = 0, voff = 0; };
+    std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>> cacheL;
+    std::map<std::pair<const Operator*, int>, std::shared_ptr<Ell>> cacheR;
+    std::vector<std::shared_ptr<Ell>> ells;
+    auto getL = [&](const Operator* O, int I, int J) {
         auto key = std::make_pair(O, I);
-        auto f = cache.find(key);
-        if (f != cache.end()) return f->second;
+        auto f = cacheL.find(key);
+        if (f != cacheL.end()) return f->second;
         auto fc = std::make_shared<FlatCsr>();
-        if (!flatten_sector(O, S, I, J, *fc)) throw Err(ERR_GENERIC, "sparse shell: unexpected dense tile");
-        cache[key] = fc; all.push_back(fc);
+        if (!flatten_sector(O, SL, I, J, *fc)) throw Err(ERR_GENERIC, "sparse shell: tile without a host copy");
+        cacheL[key] = fc;
         return fc;
     };
-    auto get_eye = [&](int I) {
-        auto f = eyeL.find(I);
-        if (f != eyeL.end()) return f->second;
-        auto fc = std::make_shared<FlatCsr>();
-        const int n = SL.size[I];
-        fc->rowptr.resize(n + 1);
-        for (int i = 0; i <= n; ++i) fc->rowptr[i] = i;
-        for (int i = 0; i < n; ++i) { fc->col.push_back(i); fc->val.push_back(1.0); }
-        eyeL[I] = fc; all.push_back(fc);
-        return fc;
+    auto getR = [&](const Operator* O, int I, int J) {
+        auto key = std::make_pair(O, I);
+        auto f = cacheR.find(key);
+        if (f != cacheR.end()) return f->second;
+        FlatCsr fc;
+        if (!flatten_sector(O, SR, I, J, fc)) throw Err(ERR_GENERIC, "sparse shell: tile without a host copy");
+        auto el = std::make_shared<Ell>();
+        const int n = SR.size[I], ns = (n + 31) / 32;
+        el->ptr.assign(ns + 1, 0);
+        for (int j = 0; j < ns; ++j) {
+            int W = 0;
+            for (int c = 32 * j; c < std::min(n, 32 * j + 32); ++c) W = std::max(W, fc.rowptr[c + 1] - fc.rowptr[c]);
+            const size_t base = el->col.size();
+            el->col.resize(base + (size_t)W * 32, 0);
+            el->val.resize(base + (size_t)W * 32, 0.0);
+            for (int c = 32 * j; c < std::min(n, 32 * j + 32); ++c)
+                for (int e = fc.rowptr[c], t = 0; e < fc.rowptr[c + 1]; ++e, ++t) { el->col[base + (size_t)t * 32 + (c - 32 * j)] = fc.col[e]; el->val[base + (size_t)t * 32 + (c - 32 * j)] = fc.val[e]; }
+            el->ptr[j + 1] = (int)el->col.size();
+        }
+        cacheR[key] = el; ells.push_back(el);
+        return el;
     };
     std::set<const void*> touched;
     auto touch = [&](const Tile& t) {
         const void* key = t.fmt == T_CSR ? (const void*)t.val : (t.fmt == T_DENSE ? (const void*)t.d : nullptr);
         if (key && touched.insert(key).second) tile_bytes += t.bytes();
     };
-    struct PendingTerm { std::shared_ptr<FlatCsr> a, b; dev::SpTerm t; };
-    std::vector<PendingTerm> pend;
+    /* entries reference their right factor by index until the device arrays exist */
+    struct PendEntry { long long src; double w; int ell; };
+    std::vector<PendEntry> pend;
     for (int p = 0; p < np; ++p) {
         const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
-        const int nL = SL.size[il], nR = SR.size[ir];
-        dev::SpPair P;
-        std::memset(&P, 0, sizeof P);
-        P.off = kron->off[p]; P.nL = nL; P.nR = nR; P.term_begin = (int)pend.size();
-        if (lr1[p] > lr0[p] && nR > 0) {
-            for (const Group& G : groups) {
-                const int jl = il + G.sA, jr = ir + G.sB;
-                if (jl < 0 || jl >= SL.nsec() || jr < 0 || jr >= SR.nsec()) continue;
-                const int q = kron->find(jl, jr);
-                if (q < 0 || SL.size[jl] == 0 || SR.size[jr] == 0) continue;
-                std::shared_ptr<FlatCsr> a = G.A ? get(cacheL, G.A, SL, il, jl) : get_eye(il);
-                if (G.A) for (const Tile& t : G.A->tiles[il]) touch(t);
-                long long annz = a->rowptr[lr1[p]] - a->rowptr[lr0[p]];
-                if (annz == 0) continue;
-                for (const RightFactor& rf : G.rights) {
-                    std::shared_ptr<FlatCsr> b;
-                    if (rf.B) {
-                        b = get(cacheR, rf.B, SR, ir, jr);
-                        for (const Tile& t : rf.B->tiles[ir]) touch(t);
-                        if (b->col.empty()) continue;
-                    }
-                    PendingTerm pt;
-                    pt.a = a; pt.b = b;
-                    std::memset(&pt.t, 0, sizeof pt.t);
-                    pt.t.xoff = kron->off[q]; pt.t.coef = rf.coef; pt.t.nRq = SR.size[jr]; pt.t.self = (q == p) ? 1 : 0;
-                    pend.push_back(pt);
-                    sp->flops += b ? 2.0 * (double)annz * (double)b->col.size() : 2.0 * (double)annz * nR;
+        const int nR = SR.size[ir];
+        if (lr1[p] <= lr0[p] || nR == 0) continue;
+        sp->max_nR = std::max(sp->max_nR, nR);
+        struct PT { std::shared_ptr<FlatCsr> a; int ell; long long xoff; int nRq; double coef; };
+        std::vector<PT> pts;
+        for (const Group& G : groups) {
+            const int jl = il + G.sA, jr = ir + G.sB;
+            if (jl < 0 || jl >= SL.nsec() || jr < 0 || jr >= SR.nsec()) continue;
+            const int q = kron->find(jl, jr);
+            if (q < 0 || SL.size[jl] == 0 || SR.size[jr] == 0) continue;
+            std::shared_ptr<FlatCsr> a;
+            if (G.A) { a = getL(G.A, il, jl); for (const Tile& t : G.A->tiles[il]) touch(t); }
+            for (const RightFactor& rf : G.rights) {
+                int ell = -1;
+                double bnnz = nR;
+                if (rf.B) {
+                    auto el = getR(rf.B, ir, jr);
+                    for (const Tile& t : rf.B->tiles[ir]) touch(t);
+                    if (el->col.empty()) continue;
+                    ell = (int)(std::find(ells.begin(), ells.end(), el) - ells.begin());
+                    bnnz = (double)el->col.size();
                 }
+                pts.push_back({a, ell, kron->off[q], SR.size[jr], rf.coef});
+                const double annz = a ? (double)(a->rowptr[lr1[p]] - a->rowptr[lr0[p]]) : (double)(lr1[p] - lr0[p]);
+                sp->flops += 2.0 * annz * bnnz;
             }
         }
-        P.term_end = (int)pend.size();
-        sp->pairs.push_back(P);
-        if (P.term_end > P.term_begin || lr1[p] > lr0[p])
-            for (int l0 = lr0[p]; l0 < lr1[p]; l0 += dev::SP_ROWS) sp->tiles.push_back({p, l0, std::min(dev::SP_ROWS, lr1[p] - l0), 0});
-        sp->max_nR = std::max(sp->max_nR, nR);
+        /* identity right factors first (plain row reads), then the gathers */
+        std::stable_sort(pts.begin(), pts.end(), [](const PT& u, const PT& v) { return (u.ell >= 0) < (v.ell >= 0); });
+        for (int l0 = lr0[p]; l0 < lr1[p]; l0 += dev::SP_ROWS) {
+            dev::SpTile tl;
+            std::memset(&tl, 0, sizeof tl);
+            tl.nR = nR; tl.nrows = std::min(dev::SP_ROWS, lr1[p] - l0);
+            tl.off = kron->off[p] + (long long)l0 * nR;
+            for (int r = 0; r < dev::SP_ROWS; ++r) {
+                tl.prog[r] = (int)pend.size();
+                if (r >= tl.nrows) continue;
+                const int l = l0 + r;
+                for (const PT& t : pts) {
+                    if (!t.a) { pend.push_back({t.xoff + (long long)l * t.nRq, t.coef, t.ell}); continue; }
+                    for (int e = t.a->rowptr[l]; e < t.a->rowptr[l + 1]; ++e) pend.push_back({t.xoff + (long long)t.a->col[e] * t.nRq, t.coef * t.a->val[e], t.ell});
+                }
+            }
+            tl.prog[dev::SP_ROWS] = (int)pend.size();
+            sp->tiles.push_back(tl);
+        }
     }
     /* widest rows first: the hardware dispatches CTAs in index order (LPT) */
-    std::stable_sort(sp->tiles.begin(), sp->tiles.end(), [&](const dev::SpTile& a, const dev::SpTile& b) { return sp->pairs[a.pair].nR > sp->pairs[b.pair].nR; });
+    std::stable_sort(sp->tiles.begin(), sp->tiles.end(), [](const dev::SpTile& a, const dev::SpTile& b) { return a.nR > b.nR; });
     if (!dry) {
         long long ni = 0, nv = 0;
-        for (auto& fc : all) { fc->ioff = ni; ni += (long long)fc->rowptr.size() + (long long)fc->col.size(); fc->voff = nv; nv += (long long)fc->val.size(); }
+        for (auto& el : ells) { el->ioff = ni; ni += (long long)el->ptr.size() + (long long)el->col.size(); el->voff = nv; nv += (long long)el->val.size(); }
         std::vector<int> hi((size_t)std::max<long long>(1, ni));
         std::vector<double> hv((size_t)std::max<long long>(1, nv));
-        for (auto& fc : all) {
-            std::copy(fc->rowptr.begin(), fc->rowptr.end(), hi.begin() + fc->ioff);
-            std::copy(fc->col.begin(), fc->col.end(), hi.begin() + fc->ioff + (long long)fc->rowptr.size());
-            std::copy(fc->val.begin(), fc->val.end(), hv.begin() + fc->voff);
+        for (auto& el : ells) {
+            std::copy(el->ptr.begin(), el->ptr.end(), hi.begin() + el->ioff);
+            std::copy(el->col.begin(), el->col.end(), hi.begin() + el->ioff + (long long)el->ptr.size());
+            std::copy(el->val.begin(), el->val.end(), hv.begin() + el->voff);
         }
         sp->d_int = std::make_shared<DevBuf>(ctx, hi.size() * 4);
         sp->d_val = std::make_shared<DevBuf>(ctx, hv.size() * 8);
@@ -242,17 +268,17 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
         dev::h2d(ctx->st, sp->d_val->p, hv.data(), hv.size() * 8);
         const int* di = sp->d_int->as<int>();
         const double* dv = sp->d_val->as<double>();
-        for (PendingTerm& pt : pend) {
-            pt.t.a_rowptr = di + pt.a->ioff; pt.t.a_col = pt.t.a_rowptr + pt.a->rowptr.size(); pt.t.a_val = dv + pt.a->voff;
-            if (pt.b) { pt.t.b_rowptr = di + pt.b->ioff; pt.t.b_col = pt.t.b_rowptr + pt.b->rowptr.size(); pt.t.b_val = dv + pt.b->voff; }
-            sp->terms.push_back(pt.t);
+        sp->entries.reserve(pend.size());
+        for (const PendEntry& pe : pend) {
+            dev::SpEntry e;
+            e.src = pe.src; e.w = pe.w; e.ell_ptr = nullptr; e.ecol = nullptr; e.eval = nullptr;
+            if (pe.ell >= 0) { const Ell& el = *ells[(size_t)pe.ell]; e.ell_ptr = di + el.ioff; e.ecol = e.ell_ptr + el.ptr.size(); e.eval = dv + el.voff; }
+            sp->entries.push_back(e);
         }
         sp->d_tiles = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->tiles.size()) * sizeof(dev::SpTile));
-        sp->d_pairs = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->pairs.size()) * sizeof(dev::SpPair));
-        sp->d_terms = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->terms.size()) * sizeof(dev::SpTerm));
+        sp->d_entries = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->entries.size()) * sizeof(dev::SpEntry));
         dev::h2d(ctx->st, sp->d_tiles->p, sp->tiles.data(), sp->tiles.size() * sizeof(dev::SpTile));
-        dev::h2d(ctx->st, sp->d_pairs->p, sp->pairs.data(), sp->pairs.size() * sizeof(dev::SpPair));
-        dev::h2d(ctx->st, sp->d_terms->p, sp->terms.data(), sp->terms.size() * sizeof(dev::SpTerm));
+        dev::h2d(ctx->st, sp->d_entries->p, sp->entries.data(), sp->entries.size() * sizeof(dev::SpEntry));
         dev::sync(ctx->st);
     }
     H->sparse = std::move(sp);
@@ -295,8 +321,7 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
     /* ---- purely sparse superblock (exact blocks handed over as CSR): one fused SpMM launch instead of the two-stage plan ---- */
     if (try_build_sparse(H.get(), kron, groups, lr0, lr1, tile_bytes, dry)) {
         if (pair_cost) {
-            const SparsePlan& sp = *H->sparse;
-            for (int p = 0; p < np; ++p) (*pair_cost)[p] = (double)(lr1[p] - lr0[p]) * SR.size[kron->pairs[p].ir] * (sp.pairs[p].term_end - sp.pairs[p].term_begin);
+            for (int p = 0; p < np; ++p) (*pair_cost)[p] = (double)(lr1[p] - lr0[p]) * SR.size[kron->pairs[p].ir];
         }
         H->alg_bytes = 16LL * H->n + tile_bytes;
         H->alg_flops = H->sparse->flops;
@@ -670,8 +695,7 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
     if (H->sparse) {
         const SparsePlan& sp = *H->sparse;
-        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_pairs->as<dev::SpPair>(), sp.d_terms->as<dev::SpTerm>(), d_x, d_y,
-                      sp.max_nR);
+        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_entries->as<dev::SpEntry>(), d_x, d_y, sp.max_nR);
         return;
     }
     H->stage1.run(H->ctx, d_x, nullptr);

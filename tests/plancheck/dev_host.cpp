@@ -86,27 +86,23 @@ void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, 
     }
 }
 
-void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpPair* pairs, const SpTerm* terms, const double* x, double* y, int) {
+void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpEntry* entries, const double* x, double* y, int) {
     ++g_launches;
     for (int w = 0; w < ntiles; ++w) {
         const SpTile& tl = tiles[w];
-        const SpPair& P = pairs[tl.pair];
-        for (int r = 0; r < tl.nrows; ++r) {
-            const int l = tl.l0 + r;
-            for (int c = 0; c < P.nR; ++c) {
+        for (int r = 0; r < tl.nrows; ++r)
+            for (int c = 0; c < tl.nR; ++c) {
                 double acc = 0.0;
-                for (int t = P.term_begin; t < P.term_end; ++t) {
-                    const SpTerm& T = terms[t];
-                    for (int e = T.a_rowptr[l]; e < T.a_rowptr[l + 1]; ++e) {
-                        const double* row = x + T.xoff + (long long)T.a_col[e] * T.nRq;
-                        const double wgt = T.coef * T.a_val[e];
-                        if (!T.b_rowptr) acc += wgt * row[c];
-                        else for (int f = T.b_rowptr[c]; f < T.b_rowptr[c + 1]; ++f) acc += wgt * T.b_val[f] * row[T.b_col[f]];
-                    }
+                for (int e = tl.prog[r]; e < tl.prog[r + 1]; ++e) {
+                    const SpEntry& E = entries[e];
+                    if (!E.ell_ptr) { acc += E.w * x[E.src + c]; continue; }
+                    const int j = c >> 5, lane = c & 31;
+                    double a = 0.0;
+                    for (int q = E.ell_ptr[j] + lane; q < E.ell_ptr[j + 1]; q += 32) a += E.eval[q] * x[E.src + E.ecol[q]];
+                    acc += E.w * a;
                 }
-                y[P.off + (long long)l * P.nR + c] = acc;
+                y[tl.off + (long long)r * tl.nR + c] = acc;
             }
-        }
     }
 }
 

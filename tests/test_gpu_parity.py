@@ -207,7 +207,7 @@ def test_sparse_sector_kernel_matches_oracle_and_chain_kernel(P, ctx, orc, nhalf
 
 
 @pytest.mark.parametrize("config,m", [("j1j2_12x6", 96), ("heis_8x4", 128), ("xy_16x8", 72)])
-def test_sparse_sector_kernel_general_csr_factors(P, ctx, orc, config, m):
+def test_sparse_sector_kernel_general_csr_factors(P, ctx, orc, config, m, monkeypatch):
     """the same kernel with BOTH factors of the L-R terms general CSR matrices and rows longer than one preload batch:
     sector-dense synthetic blocks uploaded with the dense threshold above 1, so every tile is stored as CSR."""
     import bench_workload as W
@@ -218,7 +218,9 @@ def test_sparse_sector_kernel_general_csr_factors(P, ctx, orc, config, m):
         up = pc.upload_block(P, ctx, enl_o, orc)      # the ENLARGED block handed over as CSR (route B of INTEGRATION.md)
     finally:
         ctx.set_dense_threshold(0.125)
+    monkeypatch.setenv("DMRGX_FORCE_SPARSE", "1")   # these blocks are 100 % filled inside their sectors: skip the planner's fill criterion
     shell = P.KronBlocks(up, up, [0.0]).KronSumConstruct(wl.terms)
+    monkeypatch.delenv("DMRGX_FORCE_SPARSE")
     st = shell.stats()
     assert st["tiles_stage1"] == 0 and st["tiles_stage2"] > 0          # the sparse plan is in use
     pc.check_matvec(P, orc, ctx, shell, orc.Shell(kb_o, wl.terms), np.random.default_rng(3), nvec=1)
