@@ -145,8 +145,9 @@ struct Plan {
    tiles): ONE fused launch of spmm_kernel per apply instead of the two chain launches. */
 struct SparsePlan {
     std::vector<dev::SpTile> tiles;
-    std::vector<dev::SpEntry> entries;   /* the row programs, concatenated */
-    BufRef d_tiles, d_entries, d_int, d_val;
+    std::vector<dev::SpASlot> aslots;    /* the row programs, slot-major per tile */
+    std::vector<dev::SpBSlot> bslots;
+    BufRef d_tiles, d_aslots, d_bslots, d_int, d_val;
     int max_nR = 0;
     double flops = 0;
 };

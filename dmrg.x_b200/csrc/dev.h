@@ -100,30 +100,28 @@ void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_se
 
 /* ------------------------------------------------------------------------------------------------
  *  Sparse-sector SpMM (north_star (a)): Y_p = Σ_t coef_t · A_t[IL,JL] · X_q(t) · B_t[IR,JR]ᵀ with every factor a sparse matrix
- *  (or the identity), all terms of a sector pair fused: one CTA per (pair, 8 consecutive left rows), one warp per row, lanes
- *  along the right index; the CTA's own rows of X_p are staged in shared memory by one TMA bulk copy; y is written exactly
- *  once.  At plan time the terms and the left factors are flattened into a ROW PROGRAM per output row: a short list of
- *  (source row of psi, weight, right factor) entries, so that a warp reaches its psi loads after two dependent fetches.
+ *  (or the identity), all terms of a sector pair fused: one CTA per (pair, 8 consecutive left rows), threads along the right
+ *  index with all 8 rows of their columns in registers; the CTA's own rows of X_p are staged in shared memory by one TMA bulk
+ *  copy; y is written exactly once.  At plan time the terms and the left factors are flattened into ROW PROGRAMS: short
+ *  lists of (source row of psi, weight[, right factor]) entries, so that the CTA reaches its psi loads after two dependent
+ *  fetches and has the loads of eight rows in flight together.
  * ---------------------------------------------------------------------------------------------- */
-/* One entry of a row program: acc(c) += w · Σ_f B(c, f) · x[src + col_f]   (B == identity when ell_ptr is null: acc(c) += w · x[src + c]).
-   src is the element offset in x of the source row of X_q.  B is stored as sliced ELL over the output columns: slice j holds
-   columns [32j, 32j+32), its W_j = (ell_ptr[j+1] - ell_ptr[j]) / 32 entry slots at ecol / eval[ell_ptr[j] + t*32 + lane] (padding: value 0, column 0). */
-struct SpEntry {
-    long long src;
-    double w;
-    const int* ell_ptr;
-    const int* ecol;
-    const double* eval;
-};
-constexpr int SP_ROWS = 8;          /* left rows per CTA: one warp per row */
+constexpr int SP_ROWS = 8;          /* left rows per CTA */
+/* Row programs, slot-major: slot k holds the k-th entry of EACH of the tile's 8 rows, so that a CTA issues the psi loads of
+   eight rows at once.  src = element offset in x of the source row of X_q; rows with fewer entries carry w = 0 and a valid src. */
+struct SpASlot { long long src[SP_ROWS]; double w[SP_ROWS]; };                 /* identity on the right: acc(r,c) += w_r · x[src_r + c] */
+/* a right factor B: acc(r,c) += w_r · Σ_t eval[t*ld + c] · x[src_r + ecol[t*ld + c]], t < W (ELL, slot-major over the output
+   columns: coalesced reads; padding = value 0, column 0) */
+struct SpBSlot { const int* ecol; const double* eval; int W, ld; long long src[SP_ROWS]; double w[SP_ROWS]; };
 struct SpTile {
     long long off;                  /* element offset in x and y of the tile's first row */
     int nR, nrows;
-    int prog[SP_ROWS + 1];          /* entries of row r: [prog[r], prog[r+1]) of the entry list */
-    int pad[3];
+    int a_begin, a_count;           /* SpASlot records of the tile */
+    int b_begin, b_count;           /* SpBSlot records of the tile */
+    int pad[8];
 };
 constexpr int SP_MAX_NR = 3072;     /* widest right sector the kernel stages (8 rows x 3072 doubles = 192 KB of shared memory) */
-void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpEntry* d_entries, const double* x, double* y, int max_nR);
+void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpBSlot* d_bslots, const double* x, double* y, int max_nR);
 
 /* Long accumulation chains are cut into parts that write partial tiles to the w scratch (so that a launch has enough
    equal work items to fill 148 SMs several times over); the parts are then summed in a FIXED order — deterministic,

@@ -531,20 +531,21 @@ void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d
 
 /* ================================================================================================
  *  spmm_kernel — the sparse-sector matvec (north_star (a)): un-truncated blocks, every operator factor sparse or the
- *  identity.  One CTA per (sector pair, SP_ROWS consecutive left rows), one WARP per output row, lanes along the right
- *  index, so every access to psi is a coalesced row segment and a lane keeps its 32 (strided) output columns in registers.
+ *  identity.  One CTA per (sector pair, SP_ROWS consecutive left rows); threads run along the right index and keep all
+ *  SP_ROWS rows of their (strided) columns in registers, so every access to psi is a coalesced row segment, a right
+ *  factor's (column, value) pair is fetched once and used for eight rows, and y is written exactly once.
  *    - the CTA's own rows of X_p (one contiguous range of psi) are staged in shared memory by ONE TMA bulk copy
  *      (cp.async.bulk + mbarrier; a leading / trailing element is patched by hand when the range is not 16-byte aligned);
  *      every right-factor gather X[l, col(f)] (1⊗H_R, Sz⊗Sz, ...) and every left-factor entry that falls inside the tile
  *      (the diagonal and the short-range part of H_L) is then served from shared memory;
- *    - left-factor entries outside the tile read whole rows of X_q from L2 (psi fits in L2: DRAM sees it once), 32
- *      independent coalesced loads per lane in flight;
- *    - right factors are sliced ELL (32 output columns per slice, column-major inside a slice): coalesced, branch-free reads
- *      of (column, value) pairs, no row-pointer indirection;
- *    - the row program (terms x left-factor entries, flattened at plan time) is fetched lane-parallel while the TMA copy
- *      is in flight; all terms accumulate in registers, y is written exactly once, one launch per apply.
+ *    - left-factor entries outside the tile read whole rows of X_q from L2 (psi fits in L2: DRAM sees it once); the row
+ *      programs are slot-major (k-th entry of each of the eight rows together), so 16 independent coalesced loads per thread
+ *      are in flight before the first FMA;
+ *    - right factors are slot-major ELL over the output columns: coalesced, branch-free reads, no row-pointer indirection;
+ *    - the tile's program (terms x left-factor entries, flattened at plan time) is fetched into shared memory while the TMA
+ *      copy is in flight; all terms accumulate in registers; one launch per apply.
  * ============================================================================================== */
-constexpr int SP_BD = 32 * SP_ROWS, SP_CH = 32;
+constexpr int SP_BD = 256, SP_CH = 4, SP_AMAX = 24, SP_BMAX = 8;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
@@ -566,25 +567,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     } while (!ok);
 }
 
-/* acc(c) += w · p[c] for the lane's columns c = cb0 + lane + 32 j */
-template <bool SMEM>
-__device__ __forceinline__ void sp_axpy(double (&acc)[SP_CH], const double* p, double w, int ncol) {
-#pragma unroll
-    for (int h = 0; h < SP_CH; h += 16) { /* 16 independent loads in flight per lane, then their FMAs */
-        double v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (32 * (h + j) < ncol) ? (SMEM ? p[32 * (h + j)] : __ldg(p + 32 * (h + j))) : 0.0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[h + j] += w * v[j];
-    }
-}
-
-__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpEntry* __restrict__ entries, const double* __restrict__ x,
-                                                       double* __restrict__ y) {
+__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpASlot* __restrict__ aslots, const SpBSlot* __restrict__ bslots,
+                                                       const double* __restrict__ x, double* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ unsigned long long mbar;
     __shared__ SpTile s_tile;
-    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    __shared__ SpASlot s_a[SP_AMAX];
+    __shared__ SpBSlot s_b[SP_BMAX];
+    const int tid = threadIdx.x;
     if (tid < (int)(sizeof(SpTile) / 4)) ((int*)&s_tile)[tid] = ((const int*)(tiles + blockIdx.x))[tid];
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -602,64 +592,103 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
     }
     if (tid == 32 && head) xs[0] = src0[0];
     if (tid == 64 && head + bulk < cnt) xs[cnt - 1] = src0[cnt - 1];
-    /* ---- this warp's row program, fetched while the copy is in flight ---- */
-    const int e0 = row < nrows ? s_tile.prog[row] : 0, e1 = row < nrows ? s_tile.prog[row + 1] : 0;
-    SpEntry ent;
-    ent.src = 0; ent.w = 0.0; ent.ell_ptr = nullptr; ent.ecol = nullptr; ent.eval = nullptr;
-    if (e0 + lane < e1) ent = entries[e0 + lane];
-    if (bulk > 0) mbar_wait(&mbar, 0);
-    __syncthreads();
-    if (row >= nrows) return;
     const long long tile_end = off0 + cnt;
-    for (int cb0 = 0; cb0 < nR; cb0 += 32 * SP_CH) {
-        const int ncol = nR - cb0 - lane; /* the lane owns columns cb0 + lane + 32 j while 32 j < ncol */
-        double acc[SP_CH];
+    const int na = s_tile.a_count, nb = s_tile.b_count;
+    bool staged = false;
+
+    for (int cb0 = 0; cb0 < nR; cb0 += SP_CH * SP_BD) {
+        double acc[SP_CH][SP_ROWS];
 #pragma unroll
-        for (int j = 0; j < SP_CH; ++j) acc[j] = 0.0;
-        for (int eb = e0; eb < e1; eb += 32) {
-            if (eb != e0 || cb0 != 0) { /* a later batch of a long program, or a later column pass */
-                ent.w = 0.0; ent.src = 0; ent.ell_ptr = nullptr;
-                if (eb + lane < e1) ent = entries[eb + lane];
-            }
-            const int nb = min(32, e1 - eb);
-            for (int k = 0; k < nb; ++k) {
-                const long long src = __shfl_sync(0xffffffffu, ent.src, k);
-                const double w = __shfl_sync(0xffffffffu, ent.w, k);
-                const int* ell = (const int*)__shfl_sync(0xffffffffu, (unsigned long long)ent.ell_ptr, k);
-                const bool in_tile = src >= off0 && src < tile_end;
-                if (!ell) {
-                    if (in_tile) sp_axpy<true>(acc, xs + (src - off0) + cb0 + lane, w, ncol);
-                    else sp_axpy<false>(acc, x + src + cb0 + lane, w, ncol);
-                } else {
-                    const int* ecol = (const int*)__shfl_sync(0xffffffffu, (unsigned long long)ent.ecol, k);
-                    const double* eval = (const double*)__shfl_sync(0xffffffffu, (unsigned long long)ent.eval, k);
-                    const double* gx = in_tile ? xs + (src - off0) : x + src;
-                    const int s0 = cb0 >> 5;
+        for (int j = 0; j < SP_CH; ++j)
 #pragma unroll
-                    for (int j = 0; j < SP_CH; ++j) {
-                        if (32 * j - lane >= ncol) continue; /* whole slice beyond the row (warp-uniform) */
-                        const int b0 = __ldg(ell + s0 + j), b1 = __ldg(ell + s0 + j + 1);
-                        double a = 0.0;
-                        if (in_tile) {
-#pragma unroll 4
-                            for (int q = b0 + lane; q < b1; q += 32) a += __ldg(eval + q) * gx[__ldg(ecol + q)];
-                        } else {
-#pragma unroll 4
-                            for (int q = b0 + lane; q < b1; q += 32) a += __ldg(eval + q) * __ldg(gx + __ldg(ecol + q));
-                        }
-                        acc[j] += w * a;
+            for (int r = 0; r < SP_ROWS; ++r) acc[j][r] = 0.0;
+        bool cok[SP_CH];
+#pragma unroll
+        for (int j = 0; j < SP_CH; ++j) cok[j] = cb0 + tid + j * SP_BD < nR;
+
+        /* ---- identity on the right: acc(r, c) += w_r · X_q(s_r, c) ---- */
+        for (int a0 = 0; a0 < na; a0 += SP_AMAX) {
+            const int nbatch = min(SP_AMAX, na - a0);
+            __syncthreads(); /* the previous batch has been consumed */
+            for (int i = tid; i < nbatch * (int)(sizeof(SpASlot) / 8); i += SP_BD)
+                ((double*)s_a)[i] = __ldg((const double*)(aslots + s_tile.a_begin + a0) + i);
+            if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+            __syncthreads();
+            for (int k = 0; k < nbatch; ++k) {
+#pragma unroll
+                for (int h = 0; h < SP_ROWS; h += 4) {
+                    double v[4][SP_CH];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long sr = s_a[k].src[h + r];
+                        /* a generic pointer: shared memory when the source row is one of the tile's own, L2 otherwise — no branch */
+                        const double* p = (sr >= off0 && sr < tile_end) ? (const double*)xs + (sr - off0) : x + sr;
+                        p += cb0 + tid;
+#pragma unroll
+                        for (int j = 0; j < SP_CH; ++j) v[r][j] = cok[j] ? p[j * SP_BD] : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double w = s_a[k].w[h + r];
+#pragma unroll
+                        for (int j = 0; j < SP_CH; ++j) acc[j][h + r] += w * v[r][j];
                     }
                 }
             }
         }
-        double* yr = y + off0 + (long long)row * nR + cb0 + lane;
+        /* ---- right factors: acc(r, c) += w_r · Σ_t B(c, t) · X_q(s_r, col_t(c)); B(c, t) is read once for the eight rows ---- */
+        for (int b0 = 0; b0 < nb; b0 += SP_BMAX) {
+            const int nbatch = min(SP_BMAX, nb - b0);
+            __syncthreads();
+            for (int i = tid; i < nbatch * (int)(sizeof(SpBSlot) / 8); i += SP_BD)
+                ((double*)s_b)[i] = __ldg((const double*)(bslots + s_tile.b_begin + b0) + i);
+            if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+            __syncthreads();
+            for (int k = 0; k < nbatch; ++k) {
+                const int W = s_b[k].W, ld = s_b[k].ld;
+                const int* ecol = s_b[k].ecol + cb0 + tid;
+                const double* eval = s_b[k].eval + cb0 + tid;
 #pragma unroll
-        for (int j = 0; j < SP_CH; ++j)
-            if (32 * j < ncol) yr[32 * j] = acc[j];
+                for (int h = 0; h < SP_ROWS; h += 4) {
+                    const double* gx[4];
+                    double w[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long sr = s_b[k].src[h + r];
+                        gx[r] = (sr >= off0 && sr < tile_end) ? (const double*)xs + (sr - off0) : x + sr;
+                        w[r] = s_b[k].w[h + r];
+                    }
+                    for (int t = 0; t < W; ++t) {
+                        int cf[SP_CH];
+                        double vb[SP_CH];
+#pragma unroll
+                        for (int j = 0; j < SP_CH; ++j) {
+                            cf[j] = cok[j] ? __ldg(ecol + (long long)t * ld + j * SP_BD) : 0;
+                            vb[j] = cok[j] ? __ldg(eval + (long long)t * ld + j * SP_BD) : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < SP_CH; ++j) {
+                            if (vb[j] == 0.0) continue; /* padding slot: no gather */
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) acc[j][h + r] += (w[r] * vb[j]) * gx[r][cf[j]];
+                        }
+                    }
+                }
+            }
+        }
+        if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+#pragma unroll
+        for (int r = 0; r < SP_ROWS; ++r) {
+            if (r >= nrows) continue;
+            double* yr = y + off0 + (long long)r * nR + cb0 + tid;
+#pragma unroll
+            for (int j = 0; j < SP_CH; ++j)
+                if (cok[j]) yr[j * SP_BD] = acc[j][r];
+        }
     }
 }
 
-void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpEntry* d_entries, const double* x, double* y, int max_nR) {
+void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpBSlot* d_bslots, const double* x, double* y, int max_nR) {
     if (ntiles <= 0) return;
     if (max_nR > SP_MAX_NR) throw std::runtime_error("run_spmm: right sector too wide for the shared-memory stage");
     const int smem = SP_ROWS * max_nR * 8 + 32;
@@ -667,7 +696,7 @@ void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpEntry* d_en
         CUDA_OK(cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         st->spmm_smem = smem;
     }
-    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_entries, x, y);
+    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_aslots, d_bslots, x, y);
     LAUNCH_CHECK();
 }
 

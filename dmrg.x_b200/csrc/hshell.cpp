@@ -158,7 +158,7 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
     std::unique_ptr<SparsePlan> sp(new SparsePlan());
     /* flattened factors, cached per (operator, sector): left factors stay on the host (they are folded into the row programs),
        right factors become sliced-ELL device arrays */
-    struct Ell { std::vector<int> ptr, col; std::vector<double> val; long long ioff = 0, voff = 0; };
+    struct Ell { std::vector<int> col; std::vector<double> val; int W = 0, ld = 0; long long ioff = 0, voff = 0; };
     std::map<std::pair<const Operator*, int>, std::shared_ptr<FlatCsr>> cacheL;
     std::map<std::pair<const Operator*, int>, std::shared_ptr<Ell>> cacheR;
     std::vector<std::shared_ptr<Ell>> ells;
@@ -171,6 +171,7 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
         cacheL[key] = fc;
         return fc;
     };
+    /* right factor as slot-major ELL over its rows (= the output columns): entry t of column c at [t*ld + c] */
     auto getR = [&](const Operator* O, int I, int J) {
         auto key = std::make_pair(O, I);
         auto f = cacheR.find(key);
@@ -178,18 +179,13 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
         FlatCsr fc;
         if (!flatten_sector(O, SR, I, J, fc)) throw Err(ERR_GENERIC, "sparse shell: tile without a host copy");
         auto el = std::make_shared<Ell>();
-        const int n = SR.size[I], ns = (n + 31) / 32;
-        el->ptr.assign(ns + 1, 0);
-        for (int j = 0; j < ns; ++j) {
-            int W = 0;
-            for (int c = 32 * j; c < std::min(n, 32 * j + 32); ++c) W = std::max(W, fc.rowptr[c + 1] - fc.rowptr[c]);
-            const size_t base = el->col.size();
-            el->col.resize(base + (size_t)W * 32, 0);
-            el->val.resize(base + (size_t)W * 32, 0.0);
-            for (int c = 32 * j; c < std::min(n, 32 * j + 32); ++c)
-                for (int e = fc.rowptr[c], t = 0; e < fc.rowptr[c + 1]; ++e, ++t) { el->col[base + (size_t)t * 32 + (c - 32 * j)] = fc.col[e]; el->val[base + (size_t)t * 32 + (c - 32 * j)] = fc.val[e]; }
-            el->ptr[j + 1] = (int)el->col.size();
-        }
+        const int n = SR.size[I];
+        el->ld = (n + 31) & ~31;
+        for (int c = 0; c < n; ++c) el->W = std::max(el->W, fc.rowptr[c + 1] - fc.rowptr[c]);
+        el->col.assign((size_t)el->W * el->ld, 0);
+        el->val.assign((size_t)el->W * el->ld, 0.0);
+        for (int c = 0; c < n; ++c)
+            for (int e = fc.rowptr[c], t = 0; e < fc.rowptr[c + 1]; ++e, ++t) { el->col[(size_t)t * el->ld + c] = fc.col[e]; el->val[(size_t)t * el->ld + c] = fc.val[e]; }
         cacheR[key] = el; ells.push_back(el);
         return el;
     };
@@ -198,9 +194,7 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
         const void* key = t.fmt == T_CSR ? (const void*)t.val : (t.fmt == T_DENSE ? (const void*)t.d : nullptr);
         if (key && touched.insert(key).second) tile_bytes += t.bytes();
     };
-    /* entries reference their right factor by index until the device arrays exist */
-    struct PendEntry { long long src; double w; int ell; };
-    std::vector<PendEntry> pend;
+    std::vector<int> bslot_ell; /* right factor of every SpBSlot, by index, until the device arrays exist */
     for (int p = 0; p < np; ++p) {
         const int il = kron->pairs[p].il, ir = kron->pairs[p].ir;
         const int nR = SR.size[ir];
@@ -221,32 +215,61 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
                 if (rf.B) {
                     auto el = getR(rf.B, ir, jr);
                     for (const Tile& t : rf.B->tiles[ir]) touch(t);
-                    if (el->col.empty()) continue;
+                    if (el->W == 0) continue;
                     ell = (int)(std::find(ells.begin(), ells.end(), el) - ells.begin());
-                    bnnz = (double)el->col.size();
+                    bnnz = 0;
+                    for (double v : el->val) bnnz += v != 0.0;
                 }
                 pts.push_back({a, ell, kron->off[q], SR.size[jr], rf.coef});
                 const double annz = a ? (double)(a->rowptr[lr1[p]] - a->rowptr[lr0[p]]) : (double)(lr1[p] - lr0[p]);
                 sp->flops += 2.0 * annz * bnnz;
             }
         }
-        /* identity right factors first (plain row reads), then the gathers */
-        std::stable_sort(pts.begin(), pts.end(), [](const PT& u, const PT& v) { return (u.ell >= 0) < (v.ell >= 0); });
         for (int l0 = lr0[p]; l0 < lr1[p]; l0 += dev::SP_ROWS) {
             dev::SpTile tl;
             std::memset(&tl, 0, sizeof tl);
             tl.nR = nR; tl.nrows = std::min(dev::SP_ROWS, lr1[p] - l0);
             tl.off = kron->off[p] + (long long)l0 * nR;
-            for (int r = 0; r < dev::SP_ROWS; ++r) {
-                tl.prog[r] = (int)pend.size();
-                if (r >= tl.nrows) continue;
-                const int l = l0 + r;
-                for (const PT& t : pts) {
-                    if (!t.a) { pend.push_back({t.xoff + (long long)l * t.nRq, t.coef, t.ell}); continue; }
-                    for (int e = t.a->rowptr[l]; e < t.a->rowptr[l + 1]; ++e) pend.push_back({t.xoff + (long long)t.a->col[e] * t.nRq, t.coef * t.a->val[e], t.ell});
+            /* the entries of row r in term t: (source row offset, weight) */
+            auto row_entries = [&](const PT& t, int l, std::vector<std::pair<long long, double>>& out) {
+                if (!t.a) { out.push_back({t.xoff + (long long)l * t.nRq, t.coef}); return; }
+                for (int e = t.a->rowptr[l]; e < t.a->rowptr[l + 1]; ++e) out.push_back({t.xoff + (long long)t.a->col[e] * t.nRq, t.coef * t.a->val[e]});
+            };
+            /* identity-right entries of all terms, slot-major over the rows */
+            std::vector<std::vector<std::pair<long long, double>>> al(dev::SP_ROWS);
+            for (const PT& t : pts)
+                if (t.ell < 0) for (int r = 0; r < tl.nrows; ++r) row_entries(t, l0 + r, al[r]);
+            size_t na = 0;
+            for (auto& v : al) na = std::max(na, v.size());
+            tl.a_begin = (int)sp->aslots.size(); tl.a_count = (int)na;
+            for (size_t k = 0; k < na; ++k) {
+                dev::SpASlot sl;
+                for (int r = 0; r < dev::SP_ROWS; ++r) {
+                    const bool has = k < al[r].size();
+                    sl.src[r] = has ? al[r][k].first : tl.off; sl.w[r] = has ? al[r][k].second : 0.0;
+                }
+                sp->aslots.push_back(sl);
+            }
+            /* gather slots: (term, k-th left entry of each row) */
+            tl.b_begin = (int)sp->bslots.size();
+            for (const PT& t : pts) {
+                if (t.ell < 0) continue;
+                std::vector<std::vector<std::pair<long long, double>>> bl(dev::SP_ROWS);
+                size_t nk = 0;
+                for (int r = 0; r < tl.nrows; ++r) { row_entries(t, l0 + r, bl[r]); nk = std::max(nk, bl[r].size()); }
+                for (size_t k = 0; k < nk; ++k) {
+                    dev::SpBSlot sl;
+                    std::memset(&sl, 0, sizeof sl);
+                    sl.W = ells[(size_t)t.ell]->W; sl.ld = ells[(size_t)t.ell]->ld;
+                    for (int r = 0; r < dev::SP_ROWS; ++r) {
+                        const bool has = k < bl[r].size();
+                        sl.src[r] = has ? bl[r][k].first : tl.off; sl.w[r] = has ? bl[r][k].second : 0.0;
+                    }
+                    sp->bslots.push_back(sl);
+                    bslot_ell.push_back(t.ell);
                 }
             }
-            tl.prog[dev::SP_ROWS] = (int)pend.size();
+            tl.b_count = (int)sp->bslots.size() - tl.b_begin;
             sp->tiles.push_back(tl);
         }
     }
@@ -254,31 +277,28 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
     std::stable_sort(sp->tiles.begin(), sp->tiles.end(), [](const dev::SpTile& a, const dev::SpTile& b) { return a.nR > b.nR; });
     if (!dry) {
         long long ni = 0, nv = 0;
-        for (auto& el : ells) { el->ioff = ni; ni += (long long)el->ptr.size() + (long long)el->col.size(); el->voff = nv; nv += (long long)el->val.size(); }
+        for (auto& el : ells) { el->ioff = ni; ni += (long long)el->col.size(); el->voff = nv; nv += (long long)el->val.size(); }
         std::vector<int> hi((size_t)std::max<long long>(1, ni));
         std::vector<double> hv((size_t)std::max<long long>(1, nv));
         for (auto& el : ells) {
-            std::copy(el->ptr.begin(), el->ptr.end(), hi.begin() + el->ioff);
-            std::copy(el->col.begin(), el->col.end(), hi.begin() + el->ioff + (long long)el->ptr.size());
+            std::copy(el->col.begin(), el->col.end(), hi.begin() + el->ioff);
             std::copy(el->val.begin(), el->val.end(), hv.begin() + el->voff);
         }
         sp->d_int = std::make_shared<DevBuf>(ctx, hi.size() * 4);
         sp->d_val = std::make_shared<DevBuf>(ctx, hv.size() * 8);
         dev::h2d(ctx->st, sp->d_int->p, hi.data(), hi.size() * 4);
         dev::h2d(ctx->st, sp->d_val->p, hv.data(), hv.size() * 8);
-        const int* di = sp->d_int->as<int>();
-        const double* dv = sp->d_val->as<double>();
-        sp->entries.reserve(pend.size());
-        for (const PendEntry& pe : pend) {
-            dev::SpEntry e;
-            e.src = pe.src; e.w = pe.w; e.ell_ptr = nullptr; e.ecol = nullptr; e.eval = nullptr;
-            if (pe.ell >= 0) { const Ell& el = *ells[(size_t)pe.ell]; e.ell_ptr = di + el.ioff; e.ecol = e.ell_ptr + el.ptr.size(); e.eval = dv + el.voff; }
-            sp->entries.push_back(e);
+        for (size_t i = 0; i < sp->bslots.size(); ++i) {
+            const Ell& el = *ells[(size_t)bslot_ell[i]];
+            sp->bslots[i].ecol = sp->d_int->as<int>() + el.ioff;
+            sp->bslots[i].eval = sp->d_val->as<double>() + el.voff;
         }
         sp->d_tiles = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->tiles.size()) * sizeof(dev::SpTile));
-        sp->d_entries = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->entries.size()) * sizeof(dev::SpEntry));
+        sp->d_aslots = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->aslots.size()) * sizeof(dev::SpASlot));
+        sp->d_bslots = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->bslots.size()) * sizeof(dev::SpBSlot));
         dev::h2d(ctx->st, sp->d_tiles->p, sp->tiles.data(), sp->tiles.size() * sizeof(dev::SpTile));
-        dev::h2d(ctx->st, sp->d_entries->p, sp->entries.data(), sp->entries.size() * sizeof(dev::SpEntry));
+        dev::h2d(ctx->st, sp->d_aslots->p, sp->aslots.data(), sp->aslots.size() * sizeof(dev::SpASlot));
+        dev::h2d(ctx->st, sp->d_bslots->p, sp->bslots.data(), sp->bslots.size() * sizeof(dev::SpBSlot));
         dev::sync(ctx->st);
     }
     H->sparse = std::move(sp);
@@ -695,7 +715,8 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
     if (H->sparse) {
         const SparsePlan& sp = *H->sparse;
-        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_entries->as<dev::SpEntry>(), d_x, d_y, sp.max_nR);
+        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_aslots->as<dev::SpASlot>(), sp.d_bslots->as<dev::SpBSlot>(), d_x, d_y,
+                      sp.max_nR);
         return;
     }
     H->stage1.run(H->ctx, d_x, nullptr);

@@ -86,20 +86,19 @@ void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, 
     }
 }
 
-void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpEntry* entries, const double* x, double* y, int) {
+void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpASlot* aslots, const SpBSlot* bslots, const double* x, double* y, int) {
     ++g_launches;
     for (int w = 0; w < ntiles; ++w) {
         const SpTile& tl = tiles[w];
         for (int r = 0; r < tl.nrows; ++r)
             for (int c = 0; c < tl.nR; ++c) {
                 double acc = 0.0;
-                for (int e = tl.prog[r]; e < tl.prog[r + 1]; ++e) {
-                    const SpEntry& E = entries[e];
-                    if (!E.ell_ptr) { acc += E.w * x[E.src + c]; continue; }
-                    const int j = c >> 5, lane = c & 31;
+                for (int k = 0; k < tl.a_count; ++k) { const SpASlot& S = aslots[tl.a_begin + k]; acc += S.w[r] * x[S.src[r] + c]; }
+                for (int k = 0; k < tl.b_count; ++k) {
+                    const SpBSlot& S = bslots[tl.b_begin + k];
                     double a = 0.0;
-                    for (int q = E.ell_ptr[j] + lane; q < E.ell_ptr[j + 1]; q += 32) a += E.eval[q] * x[E.src + E.ecol[q]];
-                    acc += E.w * a;
+                    for (int t = 0; t < S.W; ++t) a += S.eval[(long long)t * S.ld + c] * x[S.src[r] + S.ecol[(long long)t * S.ld + c]];
+                    acc += S.w[r] * a;
                 }
                 y[tl.off + (long long)r * tl.nR + c] = acc;
             }
