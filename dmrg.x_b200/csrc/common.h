@@ -146,8 +146,9 @@ struct Plan {
 struct SparsePlan {
     std::vector<dev::SpTile> tiles;
     std::vector<dev::SpASlot> aslots;    /* the row programs, slot-major per tile */
+    std::vector<dev::SpSSlot> sslots;
     std::vector<dev::SpBSlot> bslots;
-    BufRef d_tiles, d_aslots, d_bslots, d_int, d_val;
+    BufRef d_tiles, d_aslots, d_sslots, d_bslots, d_int, d_val;
     int max_nR = 0;
     double flops = 0;
 };

@@ -109,19 +109,23 @@ void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_se
 constexpr int SP_ROWS = 8;          /* left rows per CTA */
 /* Row programs, slot-major: slot k holds the k-th entry of EACH of the tile's 8 rows, so that a CTA issues the psi loads of
    eight rows at once.  src = element offset in x of the source row of X_q; rows with fewer entries carry w = 0 and a valid src. */
-struct SpASlot { long long src[SP_ROWS]; double w[SP_ROWS]; };                 /* identity on the right: acc(r,c) += w_r · x[src_r + c] */
-/* a right factor B: acc(r,c) += w_r · Σ_t eval[t*ld + c] · x[src_r + ecol[t*ld + c]], t < W (ELL, slot-major over the output
-   columns: coalesced reads; padding = value 0, column 0) */
-struct SpBSlot { const int* ecol; const double* eval; int W, ld; long long src[SP_ROWS]; double w[SP_ROWS]; };
+struct SpASlot { long long src[SP_ROWS]; double w[SP_ROWS]; };   /* identity on the right, source row in L2: acc(r,c) += w_r · x[src_r + c] */
+struct SpSSlot { int roff[SP_ROWS]; int pad[SP_ROWS]; double w[SP_ROWS]; }; /* the same with the source row inside the tile: acc(r,c) += w_r · xs[roff_r + c] */
+/* a right factor B: acc(r,c) += w_r · Σ_t eval[t*ld + c] · X_r[ecol[t*ld + c]], t < W (ELL, slot-major over the output
+   columns: coalesced reads; padding = value 0, column 0).  X_r = xs + roff[r] when all_in (every source row is one of the tile's
+   own: decided at plan time, no generic pointers in the kernel), else x + src[r]. */
+struct SpBSlot { const int* ecol; const double* eval; int W, ld; int all_in, pad; int roff[SP_ROWS]; long long src[SP_ROWS]; double w[SP_ROWS]; };
 struct SpTile {
     long long off;                  /* element offset in x and y of the tile's first row */
     int nR, nrows;
     int a_begin, a_count;           /* SpASlot records of the tile */
-    int b_begin, b_count;           /* SpBSlot records of the tile */
-    int pad[8];
+    int s_begin, s_count;           /* SpSSlot records */
+    int b_begin, b_count;           /* SpBSlot records */
+    int pad[6];
 };
 constexpr int SP_MAX_NR = 3072;     /* widest right sector the kernel stages (8 rows x 3072 doubles = 192 KB of shared memory) */
-void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpBSlot* d_bslots, const double* x, double* y, int max_nR);
+void run_spmm(Stream*, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpSSlot* d_sslots, const SpBSlot* d_bslots, const double* x, double* y,
+              int max_nR);
 
 /* Long accumulation chains are cut into parts that write partial tiles to the w scratch (so that a launch has enough
    equal work items to fill 148 SMs several times over); the parts are then summed in a FIXED order — deterministic,

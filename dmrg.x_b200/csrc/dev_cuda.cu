@@ -567,12 +567,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     } while (!ok);
 }
 
-__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpASlot* __restrict__ aslots, const SpBSlot* __restrict__ bslots,
-                                                       const double* __restrict__ x, double* __restrict__ y) {
+/* stage `count` records of `bytes` each from global into a shared array (all threads) */
+template <class T>
+__device__ __forceinline__ void sp_stage(T* dst, const T* src, int count, int tid) {
+    for (int i = tid; i < count * (int)(sizeof(T) / 8); i += SP_BD) ((double*)dst)[i] = __ldg((const double*)src + i);
+}
+
+__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpASlot* __restrict__ aslots, const SpSSlot* __restrict__ sslots,
+                                                       const SpBSlot* __restrict__ bslots, const double* __restrict__ x, double* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ unsigned long long mbar;
     __shared__ SpTile s_tile;
     __shared__ SpASlot s_a[SP_AMAX];
+    __shared__ SpSSlot s_s[SP_AMAX];
     __shared__ SpBSlot s_b[SP_BMAX];
     const int tid = threadIdx.x;
     if (tid < (int)(sizeof(SpTile) / 4)) ((int*)&s_tile)[tid] = ((const int*)(tiles + blockIdx.x))[tid];
@@ -592,8 +599,7 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
     }
     if (tid == 32 && head) xs[0] = src0[0];
     if (tid == 64 && head + bulk < cnt) xs[cnt - 1] = src0[cnt - 1];
-    const long long tile_end = off0 + cnt;
-    const int na = s_tile.a_count, nb = s_tile.b_count;
+    const int na = s_tile.a_count, ns = s_tile.s_count, nb = s_tile.b_count;
     bool staged = false;
 
     for (int cb0 = 0; cb0 < nR; cb0 += SP_CH * SP_BD) {
@@ -602,17 +608,17 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
         for (int j = 0; j < SP_CH; ++j)
 #pragma unroll
             for (int r = 0; r < SP_ROWS; ++r) acc[j][r] = 0.0;
+        const int c0 = cb0 + tid;
         bool cok[SP_CH];
 #pragma unroll
-        for (int j = 0; j < SP_CH; ++j) cok[j] = cb0 + tid + j * SP_BD < nR;
+        for (int j = 0; j < SP_CH; ++j) cok[j] = c0 + j * SP_BD < nR;
 
-        /* ---- identity on the right: acc(r, c) += w_r · X_q(s_r, c) ---- */
+        /* ---- identity on the right, source rows in L2: acc(r, c) += w_r · X_q(s_r, c); these loads go out first, the
+                shared-memory stage is awaited only afterwards ---- */
         for (int a0 = 0; a0 < na; a0 += SP_AMAX) {
             const int nbatch = min(SP_AMAX, na - a0);
             __syncthreads(); /* the previous batch has been consumed */
-            for (int i = tid; i < nbatch * (int)(sizeof(SpASlot) / 8); i += SP_BD)
-                ((double*)s_a)[i] = __ldg((const double*)(aslots + s_tile.a_begin + a0) + i);
-            if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+            sp_stage(s_a, aslots + s_tile.a_begin + a0, nbatch, tid);
             __syncthreads();
             for (int k = 0; k < nbatch; ++k) {
 #pragma unroll
@@ -620,12 +626,9 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
                     double v[4][SP_CH];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const long long sr = s_a[k].src[h + r];
-                        /* a generic pointer: shared memory when the source row is one of the tile's own, L2 otherwise — no branch */
-                        const double* p = (sr >= off0 && sr < tile_end) ? (const double*)xs + (sr - off0) : x + sr;
-                        p += cb0 + tid;
+                        const double* p = x + s_a[k].src[h + r] + c0;
 #pragma unroll
-                        for (int j = 0; j < SP_CH; ++j) v[r][j] = cok[j] ? p[j * SP_BD] : 0.0;
+                        for (int j = 0; j < SP_CH; ++j) v[r][j] = cok[j] ? __ldg(p + j * SP_BD) : 0.0;
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
@@ -636,51 +639,88 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
                 }
             }
         }
+        if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+        /* ---- the same with source rows inside the tile (the diagonal and the short-range part of H_L): shared memory ---- */
+        for (int a0 = 0; a0 < ns; a0 += SP_AMAX) {
+            const int nbatch = min(SP_AMAX, ns - a0);
+            __syncthreads();
+            sp_stage(s_s, sslots + s_tile.s_begin + a0, nbatch, tid);
+            __syncthreads();
+            for (int k = 0; k < nbatch; ++k) {
+#pragma unroll
+                for (int r = 0; r < SP_ROWS; ++r) {
+                    const double* p = xs + s_s[k].roff[r] + c0;
+                    const double w = s_s[k].w[r];
+#pragma unroll
+                    for (int j = 0; j < SP_CH; ++j)
+                        if (cok[j]) acc[j][r] += w * p[j * SP_BD];
+                }
+            }
+        }
         /* ---- right factors: acc(r, c) += w_r · Σ_t B(c, t) · X_q(s_r, col_t(c)); B(c, t) is read once for the eight rows ---- */
         for (int b0 = 0; b0 < nb; b0 += SP_BMAX) {
             const int nbatch = min(SP_BMAX, nb - b0);
             __syncthreads();
-            for (int i = tid; i < nbatch * (int)(sizeof(SpBSlot) / 8); i += SP_BD)
-                ((double*)s_b)[i] = __ldg((const double*)(bslots + s_tile.b_begin + b0) + i);
-            if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
+            sp_stage(s_b, bslots + s_tile.b_begin + b0, nbatch, tid);
             __syncthreads();
             for (int k = 0; k < nbatch; ++k) {
                 const int W = s_b[k].W, ld = s_b[k].ld;
-                const int* ecol = s_b[k].ecol + cb0 + tid;
-                const double* eval = s_b[k].eval + cb0 + tid;
+                const int* ecol = s_b[k].ecol + c0;
+                const double* eval = s_b[k].eval + c0;
+                if (s_b[k].all_in) {
+                    /* every source row is one of the tile's own (1⊗H_R, Sz⊗Sz, ...): gathers from shared memory, 32-bit offsets */
 #pragma unroll
-                for (int h = 0; h < SP_ROWS; h += 4) {
-                    const double* gx[4];
-                    double w[4];
+                    for (int h = 0; h < SP_ROWS; h += 4) {
+                        int roff[4];
+                        double w[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const long long sr = s_b[k].src[h + r];
-                        gx[r] = (sr >= off0 && sr < tile_end) ? (const double*)xs + (sr - off0) : x + sr;
-                        w[r] = s_b[k].w[h + r];
-                    }
-                    for (int t = 0; t < W; ++t) {
-                        int cf[SP_CH];
-                        double vb[SP_CH];
+                        for (int r = 0; r < 4; ++r) { roff[r] = s_b[k].roff[h + r]; w[r] = s_b[k].w[h + r]; }
+                        for (int t = 0; t < W; ++t) {
+                            int cf[SP_CH];
+                            double vb[SP_CH];
 #pragma unroll
-                        for (int j = 0; j < SP_CH; ++j) {
-                            cf[j] = cok[j] ? __ldg(ecol + (long long)t * ld + j * SP_BD) : 0;
-                            vb[j] = cok[j] ? __ldg(eval + (long long)t * ld + j * SP_BD) : 0.0;
+                            for (int j = 0; j < SP_CH; ++j) {
+                                cf[j] = cok[j] ? __ldg(ecol + t * ld + j * SP_BD) : 0;
+                                vb[j] = cok[j] ? __ldg(eval + t * ld + j * SP_BD) : 0.0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < SP_CH; ++j) {
+                                if (vb[j] == 0.0) continue; /* padding slot: no gather */
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc[j][h + r] += (w[r] * vb[j]) * xs[roff[r] + cf[j]];
+                            }
                         }
+                    }
+                } else {
 #pragma unroll
-                        for (int j = 0; j < SP_CH; ++j) {
-                            if (vb[j] == 0.0) continue; /* padding slot: no gather */
+                    for (int h = 0; h < SP_ROWS; h += 4) {
+                        const double* gx[4];
+                        double w[4];
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) acc[j][h + r] += (w[r] * vb[j]) * gx[r][cf[j]];
+                        for (int r = 0; r < 4; ++r) { gx[r] = x + s_b[k].src[h + r]; w[r] = s_b[k].w[h + r]; }
+                        for (int t = 0; t < W; ++t) {
+                            int cf[SP_CH];
+                            double vb[SP_CH];
+#pragma unroll
+                            for (int j = 0; j < SP_CH; ++j) {
+                                cf[j] = cok[j] ? __ldg(ecol + t * ld + j * SP_BD) : 0;
+                                vb[j] = cok[j] ? __ldg(eval + t * ld + j * SP_BD) : 0.0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < SP_CH; ++j) {
+                                if (vb[j] == 0.0) continue;
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc[j][h + r] += (w[r] * vb[j]) * __ldg(gx[r] + cf[j]);
+                            }
                         }
                     }
                 }
             }
         }
-        if (!staged) { if (bulk > 0) mbar_wait(&mbar, 0); staged = true; }
 #pragma unroll
         for (int r = 0; r < SP_ROWS; ++r) {
             if (r >= nrows) continue;
-            double* yr = y + off0 + (long long)r * nR + cb0 + tid;
+            double* yr = y + off0 + (long long)r * nR + c0;
 #pragma unroll
             for (int j = 0; j < SP_CH; ++j)
                 if (cok[j]) yr[j * SP_BD] = acc[j][r];
@@ -688,7 +728,8 @@ __global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict
     }
 }
 
-void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpBSlot* d_bslots, const double* x, double* y, int max_nR) {
+void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpASlot* d_aslots, const SpSSlot* d_sslots, const SpBSlot* d_bslots, const double* x, double* y,
+              int max_nR) {
     if (ntiles <= 0) return;
     if (max_nR > SP_MAX_NR) throw std::runtime_error("run_spmm: right sector too wide for the shared-memory stage");
     const int smem = SP_ROWS * max_nR * 8 + 32;
@@ -696,7 +737,7 @@ void run_spmm(Stream* st, const SpTile* d_tiles, int ntiles, const SpASlot* d_as
         CUDA_OK(cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         st->spmm_smem = smem;
     }
-    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_aslots, d_bslots, x, y);
+    spmm_kernel<<<ntiles, SP_BD, smem, st->s>>>(d_tiles, d_aslots, d_sslots, d_bslots, x, y);
     LAUNCH_CHECK();
 }
 

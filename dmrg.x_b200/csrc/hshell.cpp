@@ -239,16 +239,32 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
             std::vector<std::vector<std::pair<long long, double>>> al(dev::SP_ROWS);
             for (const PT& t : pts)
                 if (t.ell < 0) for (int r = 0; r < tl.nrows; ++r) row_entries(t, l0 + r, al[r]);
-            size_t na = 0;
-            for (auto& v : al) na = std::max(na, v.size());
+            /* entries whose source row is one of the tile's own rows are served from shared memory: a list of their own */
+            const long long t_end = tl.off + (long long)tl.nrows * nR;
+            std::vector<std::vector<std::pair<long long, double>>> sl_(dev::SP_ROWS), gl_(dev::SP_ROWS);
+            for (int r = 0; r < dev::SP_ROWS; ++r)
+                for (auto& e : al[r]) (e.first >= tl.off && e.first < t_end ? sl_[r] : gl_[r]).push_back(e);
+            size_t na = 0, ns = 0;
+            for (auto& v : gl_) na = std::max(na, v.size());
+            for (auto& v : sl_) ns = std::max(ns, v.size());
             tl.a_begin = (int)sp->aslots.size(); tl.a_count = (int)na;
             for (size_t k = 0; k < na; ++k) {
                 dev::SpASlot sl;
                 for (int r = 0; r < dev::SP_ROWS; ++r) {
-                    const bool has = k < al[r].size();
-                    sl.src[r] = has ? al[r][k].first : tl.off; sl.w[r] = has ? al[r][k].second : 0.0;
+                    const bool has = k < gl_[r].size();
+                    sl.src[r] = has ? gl_[r][k].first : tl.off; sl.w[r] = has ? gl_[r][k].second : 0.0;
                 }
                 sp->aslots.push_back(sl);
+            }
+            tl.s_begin = (int)sp->sslots.size(); tl.s_count = (int)ns;
+            for (size_t k = 0; k < ns; ++k) {
+                dev::SpSSlot sl;
+                std::memset(&sl, 0, sizeof sl);
+                for (int r = 0; r < dev::SP_ROWS; ++r) {
+                    const bool has = k < sl_[r].size();
+                    sl.roff[r] = has ? (int)(sl_[r][k].first - tl.off) : 0; sl.w[r] = has ? sl_[r][k].second : 0.0;
+                }
+                sp->sslots.push_back(sl);
             }
             /* gather slots: (term, k-th left entry of each row) */
             tl.b_begin = (int)sp->bslots.size();
@@ -261,9 +277,13 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
                     dev::SpBSlot sl;
                     std::memset(&sl, 0, sizeof sl);
                     sl.W = ells[(size_t)t.ell]->W; sl.ld = ells[(size_t)t.ell]->ld;
+                    sl.all_in = 1;
                     for (int r = 0; r < dev::SP_ROWS; ++r) {
                         const bool has = k < bl[r].size();
                         sl.src[r] = has ? bl[r][k].first : tl.off; sl.w[r] = has ? bl[r][k].second : 0.0;
+                        const bool in = sl.src[r] >= tl.off && sl.src[r] < tl.off + (long long)tl.nrows * nR;
+                        sl.roff[r] = in ? (int)(sl.src[r] - tl.off) : 0;
+                        sl.all_in &= in ? 1 : 0;
                     }
                     sp->bslots.push_back(sl);
                     bslot_ell.push_back(t.ell);
@@ -295,6 +315,8 @@ static bool try_build_sparse(HShell* H, const Kron* kron, const std::vector<Grou
         }
         sp->d_tiles = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->tiles.size()) * sizeof(dev::SpTile));
         sp->d_aslots = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->aslots.size()) * sizeof(dev::SpASlot));
+        sp->d_sslots = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->sslots.size()) * sizeof(dev::SpSSlot));
+        dev::h2d(ctx->st, sp->d_sslots->p, sp->sslots.data(), sp->sslots.size() * sizeof(dev::SpSSlot));
         sp->d_bslots = std::make_shared<DevBuf>(ctx, std::max<size_t>(1, sp->bslots.size()) * sizeof(dev::SpBSlot));
         dev::h2d(ctx->st, sp->d_tiles->p, sp->tiles.data(), sp->tiles.size() * sizeof(dev::SpTile));
         dev::h2d(ctx->st, sp->d_aslots->p, sp->aslots.data(), sp->aslots.size() * sizeof(dev::SpASlot));
@@ -715,7 +737,7 @@ HShell* hshell_create_product(const Kron* kron, const std::vector<std::pair<int,
 void hshell_apply(HShell* H, const double* d_x, double* d_y) {
     if (H->sparse) {
         const SparsePlan& sp = *H->sparse;
-        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_aslots->as<dev::SpASlot>(), sp.d_bslots->as<dev::SpBSlot>(), d_x, d_y,
+        dev::run_spmm(H->ctx->st, sp.d_tiles->as<dev::SpTile>(), (int)sp.tiles.size(), sp.d_aslots->as<dev::SpASlot>(), sp.d_sslots->as<dev::SpSSlot>(), sp.d_bslots->as<dev::SpBSlot>(), d_x, d_y,
                       sp.max_nR);
         return;
     }

@@ -86,7 +86,7 @@ void run_chain(Stream*, const WorkItem* items, int nitems, const Segment* segs, 
     }
 }
 
-void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpASlot* aslots, const SpBSlot* bslots, const double* x, double* y, int) {
+void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpASlot* aslots, const SpSSlot* sslots, const SpBSlot* bslots, const double* x, double* y, int) {
     ++g_launches;
     for (int w = 0; w < ntiles; ++w) {
         const SpTile& tl = tiles[w];
@@ -94,10 +94,12 @@ void run_spmm(Stream*, const SpTile* tiles, int ntiles, const SpASlot* aslots, c
             for (int c = 0; c < tl.nR; ++c) {
                 double acc = 0.0;
                 for (int k = 0; k < tl.a_count; ++k) { const SpASlot& S = aslots[tl.a_begin + k]; acc += S.w[r] * x[S.src[r] + c]; }
+                for (int k = 0; k < tl.s_count; ++k) { const SpSSlot& S = sslots[tl.s_begin + k]; acc += S.w[r] * x[tl.off + S.roff[r] + c]; }
                 for (int k = 0; k < tl.b_count; ++k) {
                     const SpBSlot& S = bslots[tl.b_begin + k];
                     double a = 0.0;
-                    for (int t = 0; t < S.W; ++t) a += S.eval[(long long)t * S.ld + c] * x[S.src[r] + S.ecol[(long long)t * S.ld + c]];
+                    const long long base = S.all_in ? tl.off + S.roff[r] : S.src[r];
+                    for (int t = 0; t < S.W; ++t) a += S.eval[(long long)t * S.ld + c] * x[base + S.ecol[(long long)t * S.ld + c]];
                     acc += S.w[r] * a;
                 }
                 y[tl.off + (long long)r * tl.nR + c] = acc;
