@@ -368,6 +368,28 @@ int dmrgx_selftest_gemm(dmrgx_ctx cx, dmrgx_int M, dmrgx_int N, dmrgx_int K, int
     });
 }
 
+int dmrgx_selftest_eig(dmrgx_ctx cx, dmrgx_int nblocks, const dmrgx_int* n, double* a, double* w, double* ms) {
+    return guard([&] {
+        Ctx* ctx = C(cx);
+        long long tot = 0, wtot = 0;
+        for (dmrgx_int b = 0; b < nblocks; ++b) { tot += n[b] * n[b]; wtot += n[b]; }
+        BufRef A = std::make_shared<DevBuf>(ctx, (size_t)std::max<long long>(1, tot) * 8), W = std::make_shared<DevBuf>(ctx, (size_t)std::max<long long>(1, wtot) * 8);
+        dev::h2d(ctx->st, A->p, a, (size_t)tot * 8);
+        std::vector<int> nn; std::vector<double*> pa, pw;
+        long long oa = 0, ow = 0;
+        for (dmrgx_int b = 0; b < nblocks; ++b) { nn.push_back((int)n[b]); pa.push_back(A->as<double>() + oa); pw.push_back(W->as<double>() + ow); oa += n[b] * n[b]; ow += n[b]; }
+        dev::sync(ctx->st);
+        const double t0 = Trace::now();
+        const int e = dev::syevd_batch(ctx->st, (int)nblocks, nn.data(), pa.data(), pw.data());
+        dev::sync(ctx->st);
+        if (ms) *ms = (Trace::now() - t0) * 1e3;
+        if (e) throw Err(ERR_GENERIC, std::string("eigensolver failed: ") + dev::last_error());
+        dev::d2h(ctx->st, a, A->p, (size_t)tot * 8);
+        dev::d2h(ctx->st, w, W->p, (size_t)wtot * 8);
+        dev::sync(ctx->st);
+    });
+}
+
 dmrgx_int dmrgx_ham_terms(dmrgx_int Lx, dmrgx_int Ly, double J1, double Jz1, double J2, double Jz2, int bcx, int bcy, dmrgx_int nsites,
                           dmrgx_int maxterms, double* a, int* iop, dmrgx_int* isite, int* jop, dmrgx_int* jsite) {
     std::vector<Term> t = ham_terms(Lx, Ly, J1, Jz1, J2, Jz2, bcx, bcy, nsites);

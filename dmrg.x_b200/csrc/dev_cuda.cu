@@ -12,22 +12,20 @@
  *  Sparse (CSR), AXPY and scaled-identity factors are accumulated into the same register tile by slow-path segments.
  *
  *  Also here: gs_pass_kernel (fused Gram-Schmidt passes of the Lanczos solver, HBM-bound, deterministic last-block
- *  reductions), jacobi_eig_kernel (batched eigensolver for reduced-density-matrix blocks of up to 64 states), the solver
- *  lanes around cuSOLVER for larger blocks, the NCCL collectives (bound lazily) and the slab-based caching allocator.
+ *  reductions), spmm_kernel (the sparse-sector matvec of un-truncated blocks, TMA-staged), the batched eigensolvers of the
+ *  reduced-density-matrix blocks (jacobi_eig_kernel up to 64 states, block Jacobi with DMMA updates above), the NCCL
+ *  collectives (bound lazily) and the slab-based caching allocator.  No vendor math library is linked.
  */
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
-#include <atomic>
 #include <chrono>
 #include <map>
 #include <unordered_map>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
-#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -57,22 +55,10 @@ struct Stream {
     int device = 0;
     cudaStream_t s = nullptr;
     bool own = false;
-    cusolverDnHandle_t solver = nullptr;
     double* partials = nullptr; /* deterministic two-stage reductions */
     unsigned int* ticket = nullptr; /* "last block finishes the reduction" counter of gs_pass */
     int* info = nullptr;
-    void* solver_work = nullptr;
-    size_t solver_work_bytes = 0;
     int num_sms = 148;
-    /* pool of solver lanes for syevd_batch: one stream + cuSOLVER handle + workspace each */
-    struct Lane {
-        cudaStream_t s = nullptr;
-        cusolverDnHandle_t h = nullptr;
-        void* work = nullptr;
-        size_t work_bytes = 0;
-        int* info = nullptr;
-    };
-    std::vector<Lane> lanes;
     std::map<size_t, std::vector<void*>> free_lists; /* caching allocator: size class -> free blocks */
     std::unordered_map<void*, size_t> live;
     size_t bytes_reserved = 0;
@@ -81,13 +67,10 @@ struct Stream {
     size_t slab_left = 0;
     double malloc_seconds = 0;   /* time spent in cudaMalloc by the caching allocator (DMRGX_TRACE prints it at the end) */
     long long malloc_calls = 0;
-    cudaEvent_t ev_main = nullptr;
-    std::vector<cudaEvent_t> ev_lane;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     int spmm_smem = 0;           /* dynamic shared memory spmm_kernel has been configured for on this device */
 };
-constexpr int SOLVER_LANES = 16;
 
 constexpr int RED_BLOCKS = 592; /* 148 SMs × 4 resident CTAs */
 constexpr int RED_MAXVEC = 40;
@@ -112,8 +95,6 @@ int init(int device, void* user_stream, Stream** out) {
         CUDA_OK(cudaMalloc(&st->info, sizeof(int) * 4));
         CUDA_OK(cudaMalloc(&st->ticket, sizeof(unsigned int)));
         CUDA_OK(cudaMemset(st->ticket, 0, sizeof(unsigned int)));
-        if (cusolverDnCreate(&st->solver) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
-        cusolverDnSetStream(st->solver, st->s);
         *out = st;
         return 0;
     } catch (const std::exception&) { return 100; }
@@ -126,16 +107,6 @@ void destroy(Stream* st) {
     cudaStreamSynchronize(st->s);
     if (getenv("DMRGX_TRACE"))
         fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved\n", st->malloc_calls, st->malloc_seconds, st->bytes_reserved / 1e9);
-    if (st->solver) cusolverDnDestroy(st->solver);
-    if (st->solver_work) cudaFree(st->solver_work);
-    for (auto& l : st->lanes) {
-        if (l.h) cusolverDnDestroy(l.h);
-        if (l.work) cudaFree(l.work);
-        if (l.info) cudaFree(l.info);
-        if (l.s) cudaStreamDestroy(l.s);
-    }
-    for (auto& e : st->ev_lane) cudaEventDestroy(e);
-    if (st->ev_main) cudaEventDestroy(st->ev_main);
     if (st->comm) comm_destroy_(st);
     for (void* q : st->slabs) cudaFree(q);
     cudaFree(st->partials);
@@ -1018,34 +989,6 @@ void gather_rows_reversed(Stream* st, const double* src, int n, int m, double* d
 }
 
 /* ================================================================================================
- *  Dense symmetric eigendecomposition of one ρ block: cuSOLVER syevd (the reference calls LAPACK
- *  through EPSLAPACK at include/DMRGBlockContainer.hpp:1976-1982 — a library call on both sides).
- *  Column-major eigenvectors of a symmetric matrix == row-major rows, which is RotMatT's layout.
- * ============================================================================================== */
-int syevd(Stream* st, int n, double* d_A, double* d_w) {
-    if (n <= 0) return 0;
-    int lwork = 0;
-    if (cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, d_A, n, d_w, &lwork) !=
-        CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnDsyevd_bufferSize failed"; return 102; }
-    const size_t need = sizeof(double) * (size_t)lwork;
-    if (need > st->solver_work_bytes) {
-        CUDA_OK(cudaStreamSynchronize(st->s));
-        if (st->solver_work) CUDA_OK(cudaFree(st->solver_work));
-        CUDA_OK(cudaMalloc(&st->solver_work, need));
-        st->solver_work_bytes = need;
-    }
-    cusolverStatus_t cs = cusolverDnDsyevd(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, d_A, n, d_w,
-                                           (double*)st->solver_work, lwork, st->info);
-    ++g_launches;
-    if (cs != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnDsyevd failed"; return 103; }
-    int info = 0;
-    CUDA_OK(cudaMemcpyAsync(&info, st->info, sizeof(int), cudaMemcpyDeviceToHost, st->s));
-    CUDA_OK(cudaStreamSynchronize(st->s));
-    if (info != 0) { g_err = "cusolverDnDsyevd: info != 0"; return 104; }
-    return 0;
-}
-
-/* ================================================================================================
  *  Collectives: NCCL, bound lazily (dlopen) so that a single-GPU process never needs the library.  In a Python
  *  process torch has already loaded its bundled libnccl.so.2 and dlopen returns that same copy.
  * ============================================================================================== */
@@ -1144,7 +1087,7 @@ void bcast_batch(Stream* st, int n, double* const* d_ptr, const long long* count
  *  eigenvector matrix in shared memory.  A round of the round-robin schedule holds n/2 disjoint index pairs; their
  *  rotations are computed from the current matrix and applied together (columns, then rows), so a sweep is n-1 rounds
  *  of fully parallel updates.  Jacobi is accurate to working precision in the small eigenvalues too, which is what the
- *  truncation ranks.  Larger blocks go to cuSOLVER's syevd on the solver lanes.
+ *  truncation ranks.  Larger blocks go to the block-Jacobi kernels below.
  *  Replaces EigRDM_BlockDiag / EPSLAPACK (include/DMRGBlockContainer.hpp:1962-2003) for these sizes.
  * ============================================================================================== */
 constexpr int JAC_NMAX = 64, JAC_LD = JAC_NMAX + 1, JAC_THREADS = 256;
@@ -1245,26 +1188,309 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const JacobiJob
     }
 }
 
-/* One worker thread per lane pulls blocks (largest first) from a shared counter: cuSOLVER's syevd synchronises with the
-   host internally, so concurrency across blocks needs concurrent host callers as well as separate streams. */
-int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, double* const* d_w) {
-    if (nblocks <= 0) return 0;
-    bool any_large = false;
-    for (int b = 0; b < nblocks; ++b) any_large = any_large || n[b] > JAC_NMAX;
-    if (any_large && st->lanes.empty()) {
-        st->lanes.resize(SOLVER_LANES);
-        st->ev_lane.resize(SOLVER_LANES);
-        CUDA_OK(cudaEventCreateWithFlags(&st->ev_main, cudaEventDisableTiming));
-        for (int i = 0; i < SOLVER_LANES; ++i) {
-            Stream::Lane& l = st->lanes[i];
-            CUDA_OK(cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking));
-            if (cusolverDnCreate(&l.h) != CUSOLVER_STATUS_SUCCESS) { g_err = "cusolverDnCreate failed"; return 101; }
-            cusolverDnSetStream(l.h, l.s);
-            CUDA_OK(cudaMalloc(&l.info, sizeof(int)));
-            CUDA_OK(cudaEventCreateWithFlags(&st->ev_lane[i], cudaEventDisableTiming));
+/* ================================================================================================
+ *  Reduced-density-matrix blocks above 64 states: batched two-sided BLOCK Jacobi, all blocks of both sides in the same
+ *  launches, no host threads, no vendor library (replaces EigRDM_BlockDiag / EPSLAPACK, include/DMRGBlockContainer.hpp:
+ *  1962-2003, for every size).  A matrix is padded to a multiple of 64 and cut into 32-wide blocks; a round of the
+ *  round-robin tournament pairs the blocks (I_k, J_k), k < nb/2:
+ *    eig_sub_kernel    one CTA per pair: the 64x64 symmetric sub-problem [[A_II, A_IJ], [A_JI, A_JJ]] is gathered into shared
+ *                      memory and diagonalised by parallel-ordered cyclic Jacobi (all angles <= pi/4, so the rotation Q_k stays
+ *                      the orthogonal matrix nearest the identity: no eigenvalue swaps, which is what makes the outer
+ *                      iteration converge); writes Q_k and the diagonalised sub-problem back;
+ *    eig_apply_kernel  FP64 DMMA: one CTA per 64x64 tile A[(I_k,J_k),(I_k',J_k')] <- Q_k^T · tile · Q_k' (k < k', the mirror
+ *                      tile is written as the transpose: A stays exactly symmetric) and per 64-column chunk of the eigenvector
+ *                      rows VT[(I_k,J_k), :] <- Q_k^T · VT[(I_k,J_k), :]; tiles whose pairs did not rotate are skipped.
+ *  A sweep is nb-1 rounds; sub-problems whose off-diagonal weight is below 1e-34 of the matrix' squared Frobenius norm do
+ *  not rotate, and a matrix is finished after a sweep without rotation (the host reads one flag per matrix per sweep of
+ *  the largest matrix).  Jacobi's accuracy in the small eigenvalues is what the truncation ranks.
+ * ============================================================================================== */
+constexpr int EB = 32;               /* block width */
+constexpr int ET = 2 * EB;           /* sub-problem / tile extent */
+constexpr int ELD = ET + 4;          /* shared-memory row stride (68 = 4 mod 16 doubles: conflict-free fragment reads both ways) */
+struct EigJob {
+    double* A;       /* np x np, row-major, padded with zeros */
+    double* VT;      /* np x np: row i = current i-th eigenvector estimate */
+    double* Q;       /* (nb/2) x 64 x 64 rotations of the current round */
+    int* rot;        /* (nb/2): the pair rotated in the current round */
+    double* outA;    /* n x n: row k = k-th eigenvector, ascending eigenvalues */
+    double* outW;    /* n */
+    double* norm2;   /* squared Frobenius norm */
+    int* active;     /* any rotation since the flag was last cleared */
+    int n, np, nb, pad;
+};
+
+/* round r of the round-robin tournament over nb (even) players: pair k = (a, b), a < b */
+__device__ __forceinline__ void eig_pair(int nb, int r, int k, int& I, int& J) {
+    const int a = k == 0 ? nb - 1 : (r + k) % (nb - 1);
+    const int b = (r + nb - 1 - k) % (nb - 1);
+    I = a < b ? a : b; J = a < b ? b : a;
+}
+
+__global__ void __launch_bounds__(256) eig_init_kernel(const EigJob* __restrict__ jobs) {
+    const EigJob jb = jobs[blockIdx.y];
+    const long long tot = (long long)jb.np * jb.np;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < tot; e += (long long)gridDim.x * 256) {
+        const int i = (int)(e / jb.np), j = (int)(e % jb.np);
+        jb.A[e] = (i < jb.n && j < jb.n) ? jb.outA[(long long)i * jb.n + j] : 0.0;
+        jb.VT[e] = i == j ? 1.0 : 0.0;
+    }
+}
+/* squared Frobenius norm, one CTA per matrix, fixed summation order (deterministic thresholds) */
+__global__ void __launch_bounds__(1024) eig_norm_kernel(const EigJob* __restrict__ jobs) {
+    const EigJob jb = jobs[blockIdx.x];
+    __shared__ double red[32];
+    double s = 0.0;
+    const long long tot = (long long)jb.n * jb.n;
+    for (long long e = threadIdx.x; e < tot; e += 1024) { const double v = jb.outA[e]; s += v * v; }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = warp_sum(red[threadIdx.x]);
+        if (threadIdx.x == 0) { *jb.norm2 = s; *jb.active = 0; }
+    }
+}
+
+/* job and local index of a CTA from the prefix table (njobs+1 entries) */
+__device__ __forceinline__ int eig_find(const int* __restrict__ prefix, int njobs, int cta, int& local) {
+    int lo = 0, hi = njobs;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= cta) lo = mid; else hi = mid; }
+    local = cta - prefix[lo];
+    return lo;
+}
+
+__global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner) {
+    extern __shared__ double jsm[];
+    double* A = jsm;                 /* [64][65] */
+    double* V = jsm + ET * JAC_LD;   /* rotation, columns = eigenvectors */
+    __shared__ double cs[ET / 2][2];
+    __shared__ int pq[ET / 2][2];
+    __shared__ double red[JAC_THREADS / 32];
+    __shared__ double offsh;
+    int k;
+    const EigJob jb = jobs[eig_find(prefix, njobs, blockIdx.x, k)];
+    const int tid = threadIdx.x, np = jb.np;
+    int I, J;
+    eig_pair(jb.nb, round % (jb.nb - 1), k, I, J);
+    for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+        const int i = e >> 6, j = e & 63;
+        const int gi = (i < EB ? I * EB + i : J * EB + i - EB), gj = (j < EB ? I * EB + j : J * EB + j - EB);
+        A[i * JAC_LD + j] = jb.A[(long long)gi * np + gj];
+        V[i * JAC_LD + j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const double thr = 1e-34 * *jb.norm2;
+    bool rotated = false;
+    for (int sweep = 0; sweep < max_inner; ++sweep) {
+        double off = 0.0;
+        for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+            const int i = e >> 6, j = e & 63;
+            const double a = A[i * JAC_LD + j];
+            if (i != j) off += a * a;
+        }
+        off = warp_sum(off);
+        if ((tid & 31) == 0) red[tid >> 5] = off;
+        __syncthreads();
+        if (tid == 0) { double o = 0; for (int w = 0; w < JAC_THREADS / 32; ++w) o += red[w]; offsh = o; }
+        __syncthreads();
+        if (offsh <= thr) break;
+        rotated = true;
+        for (int rr = 0; rr < ET - 1; ++rr) {
+            if (tid < ET / 2) {
+                const int a = tid == 0 ? ET - 1 : (rr + tid) % (ET - 1);
+                const int b = (rr + ET - 1 - tid) % (ET - 1);
+                const int p = a < b ? a : b, q = a < b ? b : a;
+                double c = 1.0, sn = 0.0;
+                const double apq = A[p * JAC_LD + q];
+                if (apq != 0.0) {
+                    const double theta = (A[q * JAC_LD + q] - A[p * JAC_LD + p]) / (2.0 * apq);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    c = 1.0 / sqrt(tt * tt + 1.0);
+                    sn = tt * c;
+                }
+                pq[tid][0] = p; pq[tid][1] = q;
+                cs[tid][0] = c; cs[tid][1] = sn;
+            }
+            __syncthreads();
+            for (int e = tid; e < (ET / 2) * ET; e += JAC_THREADS) { /* columns p, q of A and of V */
+                const int kk = e >> 6, i = e & 63;
+                const int p = pq[kk][0], q = pq[kk][1];
+                const double c = cs[kk][0], sn = cs[kk][1];
+                const double xx = A[i * JAC_LD + p], yy = A[i * JAC_LD + q];
+                A[i * JAC_LD + p] = c * xx - sn * yy; A[i * JAC_LD + q] = sn * xx + c * yy;
+                const double vx = V[i * JAC_LD + p], vy = V[i * JAC_LD + q];
+                V[i * JAC_LD + p] = c * vx - sn * vy; V[i * JAC_LD + q] = sn * vx + c * vy;
+            }
+            __syncthreads();
+            for (int e = tid; e < (ET / 2) * ET; e += JAC_THREADS) { /* rows p, q of A */
+                const int kk = e >> 6, j = e & 63;
+                const int p = pq[kk][0], q = pq[kk][1];
+                const double c = cs[kk][0], sn = cs[kk][1];
+                const double xx = A[p * JAC_LD + j], yy = A[q * JAC_LD + j];
+                A[p * JAC_LD + j] = c * xx - sn * yy; A[q * JAC_LD + j] = sn * xx + c * yy;
+            }
+            __syncthreads();
         }
     }
-    /* blocks of up to 64 states: one launch of the batched Jacobi kernel on the main stream */
+    if (tid == 0) { jb.rot[k] = rotated ? 1 : 0; if (rotated) *jb.active = 1; }
+    if (!rotated) return;
+    double* Q = jb.Q + (long long)k * ET * ET;
+    for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+        const int i = e >> 6, j = e & 63;
+        Q[e] = V[i * JAC_LD + j];
+        /* the rotated sub-problem goes back in place (symmetrised: the two triangles differ by round-off) */
+        const int gi = (i < EB ? I * EB + i : J * EB + i - EB), gj = (j < EB ? I * EB + j : J * EB + j - EB);
+        jb.A[(long long)gi * np + gj] = i == j ? A[i * JAC_LD + j] : 0.5 * (A[i * JAC_LD + j] + A[j * JAC_LD + i]);
+    }
+}
+
+/* 64x64x64 product from shared memory on the FP64 tensor pipe: acc = op(X) · Y with X(m,k) = xs[m*sxm + k*sxk], Y(k,n) = ys[k*ELD + n] */
+__device__ __forceinline__ void eig_mma64(double (&acc)[4][4][2], const double* xs, int sxm, int sxk, const double* ys, int rbase, int cbase, int g, int t) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll 4
+    for (int k0 = 0; k0 < ET; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = xs[(rbase + mi * 8 + g) * sxm + (k0 + t) * sxk];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = ys[(k0 + t) * ELD + cbase + ni * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc));
+}
+/* rows (I-block, J-block) x 64 columns starting at the two 32-column pieces c0, c1 of a row-major np-wide matrix -> smem [64][ELD] */
+__device__ __forceinline__ void eig_load_tile(double* dst, const double* M, int np, int I, int J, int c0, int c1, int tid) {
+    for (int e = tid; e < ET * (ET / 2); e += 128) { /* 16-byte pieces */
+        const int i = e >> 5, j2 = (e & 31) * 2;
+        const int gi = (i < EB ? I * EB + i : J * EB + i - EB);
+        const int gj = (j2 < EB ? c0 + j2 : c1 + j2 - EB);
+        cp_async16(dst + i * ELD + j2, M + (long long)gi * np + gj);
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) eig_apply_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round) {
+    extern __shared__ double esm[];
+    double* T0 = esm;                 /* the tile, then the intermediate */
+    double* Q0 = esm + ET * ELD;      /* Q_k  */
+    double* Q1 = esm + 2 * ET * ELD;  /* Q_k' */
+    int local;
+    const EigJob jb = jobs[eig_find(prefix, njobs, blockIdx.x, local)];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int rbase = (warp >> 1) * 32, cbase = (warp & 1) * 32;
+    const int np = jb.np, npair = jb.nb / 2, r = round % (jb.nb - 1);
+    const int ntri = npair * (npair - 1) / 2;
+    double acc[4][4][2];
+    if (local < ntri) {
+        /* ---- A tile (k < k'): T = Q_k^T · A[(I,J),(I',J')] · Q_k' ---- */
+        int k = 0, rem = local;
+        while (rem >= npair - 1 - k) { rem -= npair - 1 - k; ++k; }
+        const int k2 = k + 1 + rem;
+        const int rk = jb.rot[k], rk2 = jb.rot[k2];
+        if (!rk && !rk2) return;
+        int I, J, I2, J2;
+        eig_pair(jb.nb, r, k, I, J);
+        eig_pair(jb.nb, r, k2, I2, J2);
+        eig_load_tile(T0, jb.A, np, I, J, I2 * EB, J2 * EB, tid);
+        if (rk) for (int e = tid; e < ET * (ET / 2); e += 128) cp_async16(Q0 + (e >> 5) * ELD + (e & 31) * 2, jb.Q + (long long)k * ET * ET + (e >> 5) * ET + (e & 31) * 2);
+        if (rk2) for (int e = tid; e < ET * (ET / 2); e += 128) cp_async16(Q1 + (e >> 5) * ELD + (e & 31) * 2, jb.Q + (long long)k2 * ET * ET + (e >> 5) * ET + (e & 31) * 2);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        if (rk2) { /* T0 <- T0 · Q_k' */
+            eig_mma64(acc, T0, ELD, 1, Q1, rbase, cbase, g, t);
+            __syncthreads();
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    double* p = T0 + (rbase + mi * 8 + g) * ELD + cbase + ni * 8 + 2 * t;
+                    p[0] = acc[mi][ni][0]; p[1] = acc[mi][ni][1];
+                }
+            __syncthreads();
+        }
+        if (rk) eig_mma64(acc, Q0, 1, ELD, T0, rbase, cbase, g, t); /* Q_k^T · T0 */
+        else {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double* p = T0 + (rbase + mi * 8 + g) * ELD + cbase + ni * 8 + 2 * t;
+                    acc[mi][ni][0] = p[0]; acc[mi][ni][1] = p[1];
+                }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int i = rbase + mi * 8 + g, j = cbase + ni * 8 + 2 * t + hh;
+                    const int gi = (i < EB ? I * EB + i : J * EB + i - EB), gj = (j < EB ? I2 * EB + j : J2 * EB + j - EB);
+                    jb.A[(long long)gi * np + gj] = acc[mi][ni][hh];
+                    jb.A[(long long)gj * np + gi] = acc[mi][ni][hh]; /* the mirror tile */
+                }
+    } else {
+        /* ---- eigenvector rows: VT[(I,J), chunk] <- Q_k^T · VT[(I,J), chunk] ---- */
+        const int nchunk = np / ET;
+        const int k = (local - ntri) / nchunk, ch = (local - ntri) % nchunk;
+        if (!jb.rot[k]) return;
+        int I, J;
+        eig_pair(jb.nb, r, k, I, J);
+        eig_load_tile(T0, jb.VT, np, I, J, ch * ET, ch * ET + EB, tid);
+        for (int e = tid; e < ET * (ET / 2); e += 128) cp_async16(Q0 + (e >> 5) * ELD + (e & 31) * 2, jb.Q + (long long)k * ET * ET + (e >> 5) * ET + (e & 31) * 2);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        eig_mma64(acc, Q0, 1, ELD, T0, rbase, cbase, g, t);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int i = rbase + mi * 8 + g, j = cbase + ni * 8 + 2 * t;
+                const int gi = (i < EB ? I * EB + i : J * EB + i - EB);
+                double* p = jb.VT + (long long)gi * np + ch * ET + j;
+                p[0] = acc[mi][ni][0]; p[1] = acc[mi][ni][1];
+            }
+    }
+}
+
+/* eigenvalues = diagonal; ascending order by rank (stable on ties); row k of the output = k-th eigenvector (without the padding) */
+__global__ void __launch_bounds__(256) eig_finish_kernel(const EigJob* __restrict__ jobs, int* __restrict__ rank_ws, const int* __restrict__ rank_off) {
+    const EigJob jb = jobs[blockIdx.y];
+    int* rank_of = rank_ws + rank_off[blockIdx.y];
+    const int n = jb.n, np = jb.np;
+    /* phase 1 (block x == 0..): ranks; every CTA of the matrix computes the ranks it needs itself (n <= a few thousand) */
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const double di = jb.A[(long long)i * np + i];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) { const double dj = jb.A[(long long)j * np + j]; rk += (dj < di || (dj == di && j < i)) ? 1 : 0; }
+        rank_of[i] = rk;
+        jb.outW[rk] = di;
+    }
+}
+__global__ void __launch_bounds__(256) eig_gather_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ rank_ws, const int* __restrict__ rank_off) {
+    const EigJob jb = jobs[blockIdx.y];
+    const int* rank_of = rank_ws + rank_off[blockIdx.y];
+    const int n = jb.n, np = jb.np;
+    const long long tot = (long long)n * n;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < tot; e += (long long)gridDim.x * 256) {
+        const int i = (int)(e / n), j = (int)(e % n);
+        jb.outA[(long long)rank_of[i] * n + j] = jb.VT[(long long)i * np + j];
+    }
+}
+
+int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, double* const* d_w) {
+    if (nblocks <= 0) return 0;
+    /* blocks of up to 64 states: one launch of the single-CTA Jacobi kernel */
     {
         std::vector<JacobiJob> jobs;
         for (int b = 0; b < nblocks; ++b) if (n[b] > 0 && n[b] <= JAC_NMAX) jobs.push_back({d_A[b], d_w[b], n[b], 0});
@@ -1280,56 +1506,106 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
             free_bytes(st, d_jobs);
         }
     }
-    std::vector<int> order;
-    for (int b = 0; b < nblocks; ++b) if (n[b] > JAC_NMAX) order.push_back(b);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
-    const int nl = (int)std::min<size_t>(st->lanes.size(), order.size());
-    if (nl == 0) return 0;
-    CUDA_OK(cudaEventRecord(st->ev_main, st->s));
-    for (int i = 0; i < nl; ++i) CUDA_OK(cudaStreamWaitEvent(st->lanes[i].s, st->ev_main, 0));
-    std::atomic<int> next(0), fail(0);
-    std::string errs[SOLVER_LANES];
-    auto worker = [&](int li) {
-        cudaSetDevice(st->device);
-        Stream::Lane& l = st->lanes[li];
-        for (;;) {
-            const int k = next.fetch_add(1);
-            if (k >= (int)order.size() || fail.load()) break;
-            const int b = order[k], nb = n[b];
-            int lwork = 0;
-            if (cusolverDnDsyevd_bufferSize(l.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, d_A[b], nb, d_w[b], &lwork) !=
-                CUSOLVER_STATUS_SUCCESS) { errs[li] = "cusolverDnDsyevd_bufferSize failed"; fail = 102; break; }
-            const size_t need = sizeof(double) * (size_t)lwork;
-            if (need > l.work_bytes) {
-                cudaStreamSynchronize(l.s);
-                if (l.work) cudaFree(l.work);
-                /* grow geometrically (cudaFree synchronises the whole device): sizes creep up step by step in a sweep */
-                const size_t grow = std::max<size_t>(2 * need, (size_t)64 << 20);
-                if (cudaMalloc(&l.work, grow) != cudaSuccess) { errs[li] = "cudaMalloc of the eigensolver workspace failed"; fail = 105; break; }
-                l.work_bytes = grow;
-            }
-            if (cusolverDnDsyevd(l.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, d_A[b], nb, d_w[b], (double*)l.work, lwork,
-                                 l.info) != CUSOLVER_STATUS_SUCCESS) { errs[li] = "cusolverDnDsyevd failed"; fail = 103; break; }
-            int info = 0;
-            if (cudaMemcpyAsync(&info, l.info, sizeof(int), cudaMemcpyDeviceToHost, l.s) != cudaSuccess ||
-                cudaStreamSynchronize(l.s) != cudaSuccess) { errs[li] = "eigensolver lane: CUDA error"; fail = 106; break; }
-            if (info != 0) { errs[li] = "cusolverDnDsyevd: info != 0"; fail = 104; break; }
+    std::vector<int> big;
+    for (int b = 0; b < nblocks; ++b) if (n[b] > JAC_NMAX) big.push_back(b);
+    if (big.empty()) return 0;
+    std::stable_sort(big.begin(), big.end(), [&](int a, int b) { return n[a] > n[b]; });
+    const int nj = (int)big.size();
+    /* one workspace for everything: A, VT (np^2 each), Q (nb/2 x 64 x 64), flags */
+    std::vector<EigJob> jobs((size_t)nj);
+    size_t dbl = 0, ints = 0;
+    for (int q = 0; q < nj; ++q) {
+        EigJob& jb = jobs[(size_t)q];
+        jb.n = n[big[q]]; jb.np = (jb.n + ET - 1) / ET * ET; jb.nb = jb.np / EB; jb.pad = 0;
+        dbl += 2 * (size_t)jb.np * jb.np + (size_t)(jb.nb / 2) * ET * ET + 2;
+        ints += (size_t)(jb.nb / 2) + 2 + (size_t)jb.n;
+    }
+    double* wd = (double*)malloc_bytes(st, dbl * 8);
+    int* wi = (int*)malloc_bytes(st, (ints + 4 * (size_t)nj + 16) * 4);
+    std::vector<int> rank_off((size_t)nj);
+    {
+        double* pd = wd; int* pi = wi;
+        for (int q = 0; q < nj; ++q) {
+            EigJob& jb = jobs[(size_t)q];
+            jb.A = pd; pd += (size_t)jb.np * jb.np;
+            jb.VT = pd; pd += (size_t)jb.np * jb.np;
+            jb.Q = pd; pd += (size_t)(jb.nb / 2) * ET * ET;
+            jb.norm2 = pd; pd += 2;
+            jb.rot = pi; pi += jb.nb / 2;
+            jb.active = pi; pi += 2;
+            rank_off[(size_t)q] = (int)(pi - wi); pi += jb.n;
+            jb.outA = d_A[big[q]]; jb.outW = d_w[big[q]];
         }
-    };
-    std::vector<std::thread> th;
-    for (int i = 1; i < nl; ++i) th.emplace_back(worker, i);
-    worker(0);
-    for (auto& t : th) t.join();
-    g_launches += (long long)order.size();
-    for (int i = 0; i < nl; ++i) {
-        CUDA_OK(cudaEventRecord(st->ev_lane[i], st->lanes[i].s));
-        CUDA_OK(cudaStreamWaitEvent(st->s, st->ev_lane[i], 0));
     }
-    if (fail.load()) {
-        for (auto& e : errs) if (!e.empty()) { g_err = e; break; }
-        return fail.load();
+    int* d_tab = wi + ints;  /* prefix tables + rank offsets: 4*nj + 16 ints */
+    EigJob* d_jobs = (EigJob*)malloc_bytes(st, (size_t)nj * sizeof(EigJob));
+    CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(EigJob), cudaMemcpyHostToDevice, st->s));
+    constexpr int sub_smem = 2 * ET * JAC_LD * (int)sizeof(double), app_smem = 3 * ET * ELD * (int)sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(eig_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem));
+    CUDA_OK(cudaFuncSetAttribute(eig_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, app_smem));
+    eig_norm_kernel<<<nj, 1024, 0, st->s>>>(d_jobs);
+    LAUNCH_CHECK();
+    eig_init_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs);
+    LAUNCH_CHECK();
+    static const int max_inner = getenv("DMRGX_JAC_INNER") ? atoi(getenv("DMRGX_JAC_INNER")) : 2;
+    /* live jobs are a prefix-compacted copy of the job list (largest first); tables re-uploaded when a matrix finishes */
+    std::vector<int> live((size_t)nj);
+    for (int q = 0; q < nj; ++q) live[(size_t)q] = q;
+    std::vector<EigJob> ljobs = jobs;
+    EigJob* d_live = (EigJob*)malloc_bytes(st, (size_t)nj * sizeof(EigJob));
+    std::vector<int> h_tab((size_t)(2 * nj + 2));
+    std::vector<int> h_active((size_t)nj * 2);
+    int rc = 0;
+    int round = 0;
+    const int max_sweeps = 40;
+    while (!live.empty()) {
+        const int nl = (int)live.size();
+        int* sub_prefix = h_tab.data();
+        int* app_prefix = h_tab.data() + nl + 1;
+        sub_prefix[0] = 0; app_prefix[0] = 0;
+        int maxnb = 0;
+        for (int q = 0; q < nl; ++q) {
+            const EigJob& jb = jobs[(size_t)live[(size_t)q]];
+            ljobs[(size_t)q] = jb;
+            const int npair = jb.nb / 2;
+            sub_prefix[q + 1] = sub_prefix[q] + npair;
+            app_prefix[q + 1] = app_prefix[q] + npair * (npair - 1) / 2 + npair * (jb.np / ET);
+            maxnb = std::max(maxnb, jb.nb);
+        }
+        CUDA_OK(cudaMemcpyAsync(d_live, ljobs.data(), (size_t)nl * sizeof(EigJob), cudaMemcpyHostToDevice, st->s));
+        CUDA_OK(cudaMemcpyAsync(d_tab, h_tab.data(), (size_t)(2 * nl + 2) * 4, cudaMemcpyHostToDevice, st->s));
+        CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables are reused below */
+        /* one sweep of the largest live matrix (smaller ones complete at least one sweep of their own in the same rounds) */
+        for (int rr = 0; rr < maxnb - 1; ++rr, ++round) {
+            eig_sub_kernel<<<sub_prefix[nl], JAC_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, max_inner);
+            LAUNCH_CHECK();
+            eig_apply_kernel<<<app_prefix[nl], 128, app_smem, st->s>>>(d_live, d_tab + nl + 1, nl, round);
+            LAUNCH_CHECK();
+        }
+        /* which matrices went through the whole sweep without a rotation? */
+        for (int q = 0; q < nl; ++q) CUDA_OK(cudaMemcpyAsync(&h_active[(size_t)q], jobs[(size_t)live[(size_t)q]].active, 4, cudaMemcpyDeviceToHost, st->s));
+        CUDA_OK(cudaStreamSynchronize(st->s));
+        std::vector<int> next;
+        for (int q = 0; q < nl; ++q) if (h_active[(size_t)q]) next.push_back(live[(size_t)q]);
+        for (int q : next) CUDA_OK(cudaMemsetAsync(jobs[(size_t)q].active, 0, 4, st->s));
+        live.swap(next);
+        if (round > max_sweeps * 256 || (round / std::max(1, maxnb - 1)) > max_sweeps) { if (!live.empty()) { g_err = "block Jacobi did not converge"; rc = 107; } break; }
     }
-    return 0;
+    if (!rc) {
+        CUDA_OK(cudaMemcpyAsync(d_tab, rank_off.data(), (size_t)nj * 4, cudaMemcpyHostToDevice, st->s));
+        eig_finish_kernel<<<dim3(4, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab);
+        LAUNCH_CHECK();
+        eig_gather_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab);
+        LAUNCH_CHECK();
+    }
+    CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables and the workspace die with this scope */
+    free_bytes(st, d_live);
+    free_bytes(st, d_jobs);
+    free_bytes(st, wi);
+    free_bytes(st, wd);
+    return rc;
 }
+
+int syevd(Stream* st, int n, double* d_A, double* d_w) { return syevd_batch(st, 1, &n, &d_A, &d_w); }
 
 }  // namespace dev

@@ -172,6 +172,12 @@ dmrgx_int dmrgx_ham_terms(dmrgx_int Lx, dmrgx_int Ly, double J1, double Jz1, dou
 int dmrgx_selftest_gemm(dmrgx_ctx ctx, dmrgx_int M, dmrgx_int N, dmrgx_int K, int a_k_contig, int b_k_contig, int nseg, int reps, double* ms,
                         double* max_err);
 
+/* ---- the batched symmetric eigensolver of the truncation (EigRDM_BlockDiag, include/DMRGBlockContainer.hpp:1962-2003) on caller-supplied
+        matrices: nblocks row-major symmetric matrices of orders n[b], concatenated in `a` (host).  On return `a` holds the eigenvectors (row k of
+        block b = k-th eigenvector, ascending eigenvalues) and `w` (sum of n[b] entries) the eigenvalues; *ms = device time of the solve.
+        A test / profiling aid, not part of the reference's surface. ---- */
+int dmrgx_selftest_eig(dmrgx_ctx ctx, dmrgx_int nblocks, const dmrgx_int* n, double* a, double* w, double* ms);
+
 /* ---- device vectors (the Vec objects of the callers) ---- */
 int dmrgx_vec_alloc(dmrgx_ctx ctx, dmrgx_int n, double** d_out);
 int dmrgx_vec_free(dmrgx_ctx ctx, double* d);

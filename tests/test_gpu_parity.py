@@ -226,6 +226,44 @@ def test_sparse_sector_kernel_general_csr_factors(P, ctx, orc, config, m, monkey
     pc.check_matvec(P, orc, ctx, shell, orc.Shell(kb_o, wl.terms), np.random.default_rng(3), nvec=1)
 
 
+def _eig_selftest(P, ctx, mats):
+    import ctypes as C
+    n = np.array([m.shape[0] for m in mats], np.int64)
+    a = np.concatenate([np.ascontiguousarray(m).ravel() for m in mats])
+    w = np.zeros(int(n.sum()))
+    ms = C.c_double()
+    rc = P.lib().dmrgx_selftest_eig(ctx.h, C.c_longlong(len(mats)), n.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), C.byref(ms))
+    assert rc == 0, P.lib().dmrgx_last_error()
+    out, oa, ow = [], 0, 0
+    for k in n:
+        out.append((w[ow:ow + k], a[oa:oa + k * k].reshape(k, k)))
+        oa += k * k; ow += k
+    return out, ms.value
+
+
+@pytest.mark.parametrize("sizes", [[65, 96, 128], [130, 200, 333, 64, 17, 1], [512, 700, 257], [832, 640, 448, 250, 120, 832, 640, 448, 250, 120]],
+                         ids=["just-above-64", "mixed", "medium", "m2048-like"])
+def test_batched_block_jacobi_eigensolver(P, ctx, sizes):
+    """The library's own eigensolver for reduced-density-matrix blocks (EigRDM_BlockDiag, include/DMRGBlockContainer.hpp:1962-2003;
+    no cuSOLVER): rho-like matrices X·X^T with a fast-decaying spectrum (rank-deficient, eigenvalues down to round-off),
+    against numpy's LAPACK: eigenvalues to 1e-14 of the norm, residual and orthogonality to 1e-13."""
+    rng = np.random.default_rng(12)
+    mats = []
+    for n in sizes:
+        k = max(1, (2 * n) // 3)                                   # rank-deficient like rho_L of a wide psi block
+        X = rng.standard_normal((n, k)) * np.exp(-0.35 * np.arange(k))[None, :]
+        R = X @ X.T
+        mats.append(R / np.trace(R))
+    res, ms = _eig_selftest(P, ctx, mats)
+    for (w, V), R in zip(res, mats):
+        ref = np.linalg.eigvalsh(R)
+        nrm = np.abs(ref).max()
+        assert np.all(np.diff(w) >= 0)
+        assert np.abs(w - ref).max() <= 1e-14 * nrm + 1e-17
+        assert np.abs(V @ V.T - np.eye(len(w))).max() <= 1e-13          # rows orthonormal
+        assert np.abs(V @ R @ V.T - np.diag(w)).max() <= 1e-14 * nrm + 1e-17
+
+
 def test_sparse_and_dense_tile_paths_agree(P, ctx, orc):
     rng = np.random.default_rng(11)
     ham = J1J2_CYL
