@@ -397,6 +397,10 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
     /* ---- pre-summed right factors per (group, right row sector) ---- */
     struct BTile { Tile t; double coef; };
     std::vector<std::vector<std::vector<BTile>>> bt(groups.size(), std::vector<std::vector<BTile>>(SR.nsec()));
+    /* An operator of the enlarged block is O_i ⊗ 1_site: the SAME panel is referenced from two enlarged sectors (site up / site
+       down).  Sums over the same source panels with the same coefficients are therefore materialised once and shared
+       (halves the derived panels: 185 -> 93 MB at 12x6 m = 2048, less DRAM traffic and L2 pressure in stage 2). */
+    std::map<std::vector<std::pair<const double*, double>>, BufRef> sum_cache;
     for (size_t g = 0; g < groups.size(); ++g) {
         const Group& G = groups[g];
         for (int ir = 0; ir < SR.nsec(); ++ir) {
@@ -425,12 +429,16 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
                 const long long cnt = (long long)raw[a].t.nr * raw[a].t.nc;
                 BTile merged = raw[a];
                 if (!dry) {
-                    BufRef sum = std::make_shared<DevBuf>(ctx, cnt * 8);
-                    for (size_t k = 0; k < same.size(); ++k) {
-                        const BTile& s = raw[same[k]];
-                        dev::axpby_out(ctx->st, k == 0 ? nullptr : sum->as<double>(), s.t.d, s.coef, sum->as<double>(), cnt);
+                    std::vector<std::pair<const double*, double>> key;
+                    for (size_t k = 0; k < same.size(); ++k) key.push_back({raw[same[k]].t.d, raw[same[k]].coef});
+                    std::sort(key.begin(), key.end());
+                    BufRef& sum = sum_cache[key];
+                    if (!sum) {
+                        sum = std::make_shared<DevBuf>(ctx, cnt * 8);
+                        for (size_t k = 0; k < key.size(); ++k)
+                            dev::axpby_out(ctx->st, k == 0 ? nullptr : sum->as<double>(), key[k].first, key[k].second, sum->as<double>(), cnt);
+                        H->keep.push_back(sum);
                     }
-                    H->keep.push_back(sum);
                     merged.t.d = sum->as<double>(); merged.t.owner = sum;
                 }
                 merged.coef = 1.0;
