@@ -1463,16 +1463,31 @@ __global__ void __launch_bounds__(128, 2) eig_apply_kernel(const EigJob* __restr
     }
 }
 
-/* eigenvalues = diagonal; ascending order by rank (stable on ties); row k of the output = k-th eigenvector (without the padding) */
-__global__ void __launch_bounds__(256) eig_finish_kernel(const EigJob* __restrict__ jobs, int* __restrict__ rank_ws, const int* __restrict__ rank_off) {
+/* Eigenvalues as Rayleigh quotients with the ORIGINAL matrix, lambda_k = v_k · (A0 v_k): the diagonal of the iterated matrix
+   carries the rounding of every DMMA update (about sqrt(64)·eps per round, 1e-14 after a few dozen rounds), the quotient
+   only that of one product.  T = VT · A0 was written over jb.A by a chain launch; one warp per eigenvector. */
+__global__ void __launch_bounds__(256) eig_rq_kernel(const EigJob* __restrict__ jobs, double* __restrict__ lam_ws, const int* __restrict__ lam_off) {
+    const EigJob jb = jobs[blockIdx.y];
+    double* lam = lam_ws + lam_off[blockIdx.y];
+    const int n = jb.n, np = jb.np, lane = threadIdx.x & 31;
+    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < n; k += gridDim.x * 8) {
+        double s = 0.0;
+        for (int j = lane; j < n; j += 32) s += jb.A[(long long)k * np + j] * jb.VT[(long long)k * np + j];
+        s = warp_sum(s);
+        if (lane == 0) lam[k] = s;
+    }
+}
+/* ascending order by rank (stable on ties); row k of the output = k-th eigenvector (without the padding) */
+__global__ void __launch_bounds__(256) eig_finish_kernel(const EigJob* __restrict__ jobs, const double* __restrict__ lam_ws, const int* __restrict__ lam_off,
+                                                         int* __restrict__ rank_ws, const int* __restrict__ rank_off) {
     const EigJob jb = jobs[blockIdx.y];
     int* rank_of = rank_ws + rank_off[blockIdx.y];
-    const int n = jb.n, np = jb.np;
-    /* phase 1 (block x == 0..): ranks; every CTA of the matrix computes the ranks it needs itself (n <= a few thousand) */
+    const double* lam = lam_ws + lam_off[blockIdx.y];
+    const int n = jb.n;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const double di = jb.A[(long long)i * np + i];
+        const double di = lam[i];
         int rk = 0;
-        for (int j = 0; j < n; ++j) { const double dj = jb.A[(long long)j * np + j]; rk += (dj < di || (dj == di && j < i)) ? 1 : 0; }
+        for (int j = 0; j < n; ++j) { const double dj = lam[j]; rk += (dj < di || (dj == di && j < i)) ? 1 : 0; }
         rank_of[i] = rk;
         jb.outW[rk] = di;
     }
@@ -1517,12 +1532,13 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     for (int q = 0; q < nj; ++q) {
         EigJob& jb = jobs[(size_t)q];
         jb.n = n[big[q]]; jb.np = (jb.n + ET - 1) / ET * ET; jb.nb = jb.np / EB; jb.pad = 0;
-        dbl += 2 * (size_t)jb.np * jb.np + (size_t)(jb.nb / 2) * ET * ET + 2;
+        dbl += 2 * (size_t)jb.np * jb.np + (size_t)(jb.nb / 2) * ET * ET + 2 + (size_t)jb.n;
         ints += (size_t)(jb.nb / 2) + 2 + (size_t)jb.n;
     }
     double* wd = (double*)malloc_bytes(st, dbl * 8);
     int* wi = (int*)malloc_bytes(st, (ints + 4 * (size_t)nj + 16) * 4);
     std::vector<int> rank_off((size_t)nj);
+    std::vector<long long> lam_off((size_t)nj);
     {
         double* pd = wd; int* pi = wi;
         for (int q = 0; q < nj; ++q) {
@@ -1531,6 +1547,7 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
             jb.VT = pd; pd += (size_t)jb.np * jb.np;
             jb.Q = pd; pd += (size_t)(jb.nb / 2) * ET * ET;
             jb.norm2 = pd; pd += 2;
+            lam_off[(size_t)q] = pd - wd; pd += jb.n;
             jb.rot = pi; pi += jb.nb / 2;
             jb.active = pi; pi += 2;
             rank_off[(size_t)q] = (int)(pi - wi); pi += jb.n;
@@ -1591,14 +1608,49 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         live.swap(next);
         if (round > max_sweeps * 256 || (round / std::max(1, maxnb - 1)) > max_sweeps) { if (!live.empty()) { g_err = "block Jacobi did not converge"; rc = 107; } break; }
     }
+    WorkItem* d_items = nullptr;
+    Segment* d_segs = nullptr;
     if (!rc) {
+        /* T = VT[0:n, 0:n] · A0 over jb.A (the iterated matrix is no longer needed), on the chain kernel */
+        std::vector<WorkItem> items;
+        std::vector<Segment> segs;
+        for (int q = 0; q < nj; ++q) {
+            const EigJob& jb = jobs[(size_t)q];
+            Segment sg;
+            std::memset(&sg, 0, sizeof sg);
+            sg.type = SEG_GEMM; sg.coef = 1.0; sg.K = jb.n;
+            sg.A = jb.VT; sg.lda_m = jb.np; sg.lda_k = 1;
+            sg.B = jb.outA; sg.ldb_n = 1; sg.ldb_k = jb.n;
+            segs.push_back(sg);
+            for (int m0 = 0; m0 < jb.n; m0 += TILE)
+                for (int n0 = 0; n0 < jb.n; n0 += TILE) {
+                    WorkItem it;
+                    std::memset(&it, 0, sizeof it);
+                    it.C = jb.A + (long long)m0 * jb.np + n0; it.ldc = jb.np; it.m0 = m0; it.n0 = n0;
+                    it.tm = std::min(TILE, jb.n - m0); it.tn = std::min(TILE, jb.n - n0);
+                    it.seg_begin = q; it.seg_end = q + 1;
+                    items.push_back(it);
+                }
+        }
+        d_items = (WorkItem*)malloc_bytes(st, items.size() * sizeof(WorkItem));
+        d_segs = (Segment*)malloc_bytes(st, segs.size() * sizeof(Segment));
+        CUDA_OK(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st->s));
+        CUDA_OK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, st->s));
+        for (int q = 0; q < nj; ++q) h_tab[(size_t)q] = (int)lam_off[(size_t)q];
         CUDA_OK(cudaMemcpyAsync(d_tab, rank_off.data(), (size_t)nj * 4, cudaMemcpyHostToDevice, st->s));
-        eig_finish_kernel<<<dim3(4, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab);
+        CUDA_OK(cudaMemcpyAsync(d_tab + nj, h_tab.data(), (size_t)nj * 4, cudaMemcpyHostToDevice, st->s));
+        run_chain(st, d_items, (int)items.size(), d_segs, nullptr, nullptr, nullptr);
+        eig_rq_kernel<<<dim3(16, nj), 256, 0, st->s>>>(d_jobs, wd, d_tab + nj);
+        LAUNCH_CHECK();
+        eig_finish_kernel<<<dim3(4, nj), 256, 0, st->s>>>(d_jobs, wd, d_tab + nj, wi, d_tab);
         LAUNCH_CHECK();
         eig_gather_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab);
         LAUNCH_CHECK();
+        CUDA_OK(cudaStreamSynchronize(st->s)); /* the host item lists must outlive their copies */
     }
     CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables and the workspace die with this scope */
+    free_bytes(st, d_items);
+    free_bytes(st, d_segs);
     free_bytes(st, d_live);
     free_bytes(st, d_jobs);
     free_bytes(st, wi);
