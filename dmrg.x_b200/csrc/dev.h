@@ -154,6 +154,11 @@ void multiaxpy(Stream*, const double* V, long long ldv, int nvec, const double* 
    if d_dots: d_dots[i] = V_i·w (i < nvec);   if d_nrm2: *d_nrm2 = w·w.   nvec <= 40. */
 constexpr int MAX_BASIS = 39; /* largest ncv the fused kernels take (eigs_smallest validates -H_eps_ncv against it) */
 void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long long n, const double* d_coef, double* d_dots, double* d_nrm2);
+/* Last step of the two-pass Gram-Schmidt, fused with the normalisation (no reduction, no all-reduce):
+       vout = (w - Σ_i d_coef[i]·V_i) / sqrt(b2),   b2 = *d_nrm2_in - Σ_i d_coef[i]²   (Pythagoras: d_nrm2_in is ||w||² BEFORE the update
+   and the coefficients of a second pass are round-off sized, so there is no cancellation);  *d_nrm2_out = b2.  nvec <= MAX_BASIS + 1. */
+void gs_final(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, const double* d_coef, const double* d_nrm2_in,
+              double* d_nrm2_out, double* vout);
 /* v = w / sqrt(*d_nrm2) */
 void scale_inv_norm(Stream*, const double* w, const double* d_nrm2, double* v, long long n);
 /* in place: V_a <- Σ_i S[i*kk+a] V_i  (i < ncv, a < kk), S on the device */

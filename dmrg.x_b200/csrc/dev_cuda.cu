@@ -909,6 +909,47 @@ void gs_pass(Stream* st, const double* V, long long ldv, int nvec, double* w, lo
     LAUNCH_CHECK();
 }
 
+template <int NV>
+__global__ void __launch_bounds__(256) gs_final_kernel(const double* __restrict__ V, long long ldv, int nvec, const double* __restrict__ w, long long n,
+                                                       const double* __restrict__ coef, const double* __restrict__ nrm2_in, double* __restrict__ nrm2_out,
+                                                       double* __restrict__ vout) {
+    __shared__ double c[NV];
+    __shared__ double inv;
+    if (threadIdx.x < NV) c[threadIdx.x] = threadIdx.x < nvec ? coef[threadIdx.x] : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nvec; ++i) s += c[i] * c[i]; /* fixed order: every block (and every rank) gets the same bits */
+        double b2 = *nrm2_in - s;
+        if (!(b2 > 0.0)) b2 = 0.0;
+        inv = b2 > 0.0 ? 1.0 / sqrt(b2) : 0.0;
+        if (blockIdx.x == 0) *nrm2_out = b2;
+    }
+    __syncthreads();
+    const double sc = inv;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        double acc = w[q];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < nvec) acc -= c[i] * V[i * ldv + q];
+        vout[q] = acc * sc;
+    }
+}
+void gs_final(Stream* st, const double* V, long long ldv, int nvec, const double* w, long long n, const double* d_coef, const double* d_nrm2_in,
+              double* d_nrm2_out, double* vout) {
+    if (nvec > RED_MAXVEC) throw std::runtime_error("gs_final: too many basis vectors");
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, RED_BLOCKS));
+#define GF_LAUNCH(NV) gs_final_kernel<NV><<<blocks, 256, 0, st->s>>>(V, ldv, nvec, w, n, d_coef, d_nrm2_in, d_nrm2_out, vout)
+    if (nvec <= 4) GF_LAUNCH(4);
+    else if (nvec <= 8) GF_LAUNCH(8);
+    else if (nvec <= 12) GF_LAUNCH(12);
+    else if (nvec <= 17) GF_LAUNCH(17);
+    else if (nvec <= 24) GF_LAUNCH(24);
+    else GF_LAUNCH(40);
+#undef GF_LAUNCH
+    LAUNCH_CHECK();
+}
+
 __global__ void scale_inv_norm_kernel(const double* __restrict__ w, const double* __restrict__ nrm2, double* __restrict__ v, long long n) {
     const double inv = 1.0 / sqrt(*nrm2);
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) v[q] = w[q] * inv;
@@ -1532,7 +1573,7 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     for (int q = 0; q < nj; ++q) {
         EigJob& jb = jobs[(size_t)q];
         jb.n = n[big[q]]; jb.np = (jb.n + ET - 1) / ET * ET; jb.nb = jb.np / EB; jb.pad = 0;
-        dbl += 2 * (size_t)jb.np * jb.np + (size_t)(jb.nb / 2) * ET * ET + 2 + (size_t)jb.n;
+        dbl += 2 * (size_t)jb.np * jb.np + (size_t)(jb.nb / 2) * ET * ET + 2 + (size_t)jb.np; /* every piece a multiple of 2 doubles: 16-byte cp.async */
         ints += (size_t)(jb.nb / 2) + 2 + (size_t)jb.n;
     }
     double* wd = (double*)malloc_bytes(st, dbl * 8);
@@ -1547,7 +1588,7 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
             jb.VT = pd; pd += (size_t)jb.np * jb.np;
             jb.Q = pd; pd += (size_t)(jb.nb / 2) * ET * ET;
             jb.norm2 = pd; pd += 2;
-            lam_off[(size_t)q] = pd - wd; pd += jb.n;
+            lam_off[(size_t)q] = pd - wd; pd += jb.np;
             jb.rot = pi; pi += jb.nb / 2;
             jb.active = pi; pi += 2;
             rank_off[(size_t)q] = (int)(pi - wi); pi += jb.n;

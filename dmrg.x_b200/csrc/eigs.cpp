@@ -68,8 +68,9 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     BufRef wbuf = std::make_shared<DevBuf>(ctx, (size_t)std::max<long long>(1, N) * 8);
     BufRef xfull = dist ? std::make_shared<DevBuf>(ctx, (size_t)NG * 8) : nullptr;
     /* coefficient table: one row per Lanczos step of a restart cycle = {pass-1 coefficients (ld+1), pass-2 coefficients
-       (ld+1), ||w||^2}.  It is read back ONCE per cycle: the steps of a cycle are queued without any host round trip. */
-    const int RW = 2 * (ld + 1) + 1;
+       (ld+1), ||w'||^2 after the first pass, beta^2 = ||w''||^2}.  It is read back ONCE per cycle: the steps of a cycle are queued
+       without any host round trip. */
+    const int RW = 2 * (ld + 1) + 2;
     BufRef scal = std::make_shared<DevBuf>(ctx, (size_t)(ld * RW + 2 + ld * ld) * 8);
     double* V = basis->as<double>();
     double* w = wbuf->as<double>();
@@ -107,7 +108,7 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
                     T[(size_t)i * ld + j] = c;
                     T[(size_t)j * ld + i] = c;
                 }
-                const double b = std::sqrt(std::max(0.0, r[2 * (ld + 1)]));
+                const double b = std::sqrt(std::max(0.0, r[2 * (ld + 1) + 1]));
                 beta_last = b;
                 if (!(b >= 1e-14)) { nc = j + 1; invariant = true; absorbed = upto; return true; }
             }
@@ -122,18 +123,20 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
                 hshell_apply(H, V + (size_t)j * N, w);
             }
             stats.nmatvec++;
-            /* classical Gram-Schmidt against the whole basis, twice, as three fused passes (dots | update+dots | update+norm);
-               the coefficients stay on the device until the end of the cycle */
+            /* classical Gram-Schmidt against the whole basis, twice, as three fused passes over the basis with TWO reductions:
+                 dots  |  update + dots + ||w'||^2  |  update + normalise,
+               the last norm by Pythagoras, ||w''||^2 = ||w'||^2 - |h2|^2 (the second-pass coefficients are round-off sized: no
+               cancellation), so the third pass needs no reduction — on several GPUs two all-reduces per step instead of three.
+               The coefficients stay on the device until the end of the cycle. */
             double* d_h = d_tab + (size_t)j * RW;
             double* d_h2 = d_h + (ld + 1);
-            double* d_n = d_h2 + (ld + 1);
+            double* d_n = d_h2 + (ld + 1);   /* ||w'||^2, directly behind the pass-2 coefficients: one all-reduce covers both */
+            double* d_b2 = d_n + 1;
             dev::gs_pass(st, V, N, j + 1, w, N, nullptr, d_h, nullptr);
             dev::allreduce_sum(st, d_h, j + 1);
-            dev::gs_pass(st, V, N, j + 1, w, N, d_h, d_h2, nullptr);
-            dev::allreduce_sum(st, d_h2, j + 1);
-            dev::gs_pass(st, V, N, j + 1, w, N, d_h2, nullptr, d_n);
-            dev::allreduce_sum(st, d_n, 1);
-            dev::scale_inv_norm(st, w, d_n, V + (size_t)(j + 1) * N, N);
+            dev::gs_pass(st, V, N, j + 1, w, N, d_h, d_h2, d_n);
+            if (dist) dev::allreduce_sum(st, d_h2, (ld + 1) + 1);
+            dev::gs_final(st, V, N, j + 1, w, N, d_h2, d_n, d_b2, V + (size_t)(j + 1) * N);
             /* On large superblocks (a matvec costs far more than a host round trip) the stopping test is also made inside the
                cycle, after every step from the second new one on, instead of only at the restart boundary: saves the 4 or so
                matvecs a converged solve would otherwise still run to fill the basis. */

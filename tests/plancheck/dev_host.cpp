@@ -149,6 +149,17 @@ void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long 
     if (dots) for (int i = 0; i < nvec; ++i) { double s = 0; for (long long q = 0; q < n; ++q) s += V[i * ldv + q] * w[q]; dots[i] = s; }
     if (nrm2) { double s = 0; for (long long q = 0; q < n; ++q) s += w[q] * w[q]; *nrm2 = s; }
 }
+void gs_final(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, const double* coef, const double* nrm2_in, double* nrm2_out,
+              double* vout) {
+    ++g_launches;
+    double s = 0;
+    for (int i = 0; i < nvec; ++i) s += coef[i] * coef[i];
+    double b2 = *nrm2_in - s;
+    if (!(b2 > 0.0)) b2 = 0.0;
+    const double inv = b2 > 0.0 ? 1.0 / std::sqrt(b2) : 0.0;
+    *nrm2_out = b2;
+    for (long long q = 0; q < n; ++q) { double a = w[q]; for (int i = 0; i < nvec; ++i) a -= coef[i] * V[i * ldv + q]; vout[q] = a * inv; }
+}
 void scale_inv_norm(Stream*, const double* w, const double* nrm2, double* v, long long n) {
     ++g_launches;
     const double inv = 1.0 / std::sqrt(*nrm2);
