@@ -66,7 +66,10 @@ int dmrgx_ctx_create_dist(int device, void* stream, int rank, int world, const v
     return 0;
 }
 int dmrgx_ctx_rank(dmrgx_ctx ctx, int* rank, int* world) { *rank = C(ctx)->rank; *world = C(ctx)->world; return 0; }
-int dmrgx_ctx_destroy(dmrgx_ctx ctx) { if (!ctx) return 0; return guard([&] { dev::destroy(C(ctx)->st); delete C(ctx); }); }
+int dmrgx_ctx_destroy(dmrgx_ctx ctx) {
+    if (!ctx) return 0;
+    return guard([&] { Ctx* c = C(ctx); dev::destroy(c->st); c->st = nullptr; delete c; }); /* (the handle is looked up ONCE: it dies here) */
+}
 int dmrgx_ctx_sync(dmrgx_ctx ctx) { return guard([&] { dev::sync(C(ctx)->st); }); }
 int dmrgx_ctx_set_dense_threshold(dmrgx_ctx ctx, double fill) { C(ctx)->dense_fill_threshold = fill; return 0; }
 

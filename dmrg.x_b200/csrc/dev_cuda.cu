@@ -1320,7 +1320,10 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
         V[i * JAC_LD + j] = i == j ? 1.0 : 0.0;
     }
     __syncthreads();
-    const double thr = 1e-34 * *jb.norm2;
+    /* A sub-problem rotates while its off-diagonal weight exceeds the noise the FP64 DMMA updates leave in it (about
+       sqrt(64)·eps of the matrix norm per element and round): off(S) <= 3e-14·||A||_F.  The eigenvalues are afterwards taken as
+       Rayleigh quotients with the original matrix, which squares this error. */
+    const double thr = 1e-27 * *jb.norm2;
     bool rotated = false;
     for (int sweep = 0; sweep < max_inner; ++sweep) {
         double off = 0.0;
@@ -1343,11 +1346,16 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
                 const int p = a < b ? a : b, q = a < b ? b : a;
                 double c = 1.0, sn = 0.0;
                 const double apq = A[p * JAC_LD + q];
-                if (apq != 0.0) {
-                    const double theta = (A[q * JAC_LD + q] - A[p * JAC_LD + p]) / (2.0 * apq);
-                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    c = 1.0 / sqrt(tt * tt + 1.0);
-                    sn = tt * c;
+                /* the rotation with |angle| <= pi/4 that zeroes a_pq, with two dependent special functions instead of five
+                   (a division and a square root cost ~300 cycles each in FP64 and this step is serial):
+                   d = a_qq - a_pp, b = 2 a_pq, h = hypot(d, b):  c^2 = (h + |d|) / 2h,  s = sgn(d) b / (2 h c) */
+                const double d = A[q * JAC_LD + q] - A[p * JAC_LD + p], b2 = 2.0 * apq;
+                const double hh = d * d + b2 * b2;
+                if (apq != 0.0 && hh > 1e-290) {
+                    const double rh = rsqrt(hh);
+                    const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+                    c = sqrt(c2);
+                    sn = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * rsqrt(c2);
                 }
                 pq[tid][0] = p; pq[tid][1] = q;
                 cs[tid][0] = c; cs[tid][1] = sn;
@@ -1512,10 +1520,11 @@ __global__ void __launch_bounds__(256) eig_rq_kernel(const EigJob* __restrict__ 
     double* lam = lam_ws + lam_off[blockIdx.y];
     const int n = jb.n, np = jb.np, lane = threadIdx.x & 31;
     for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < n; k += gridDim.x * 8) {
-        double s = 0.0;
-        for (int j = lane; j < n; j += 32) s += jb.A[(long long)k * np + j] * jb.VT[(long long)k * np + j];
-        s = warp_sum(s);
-        if (lane == 0) lam[k] = s;
+        double s = 0.0, vv = 0.0;
+        for (int j = lane; j < n; j += 32) { const double v = jb.VT[(long long)k * np + j]; s += jb.A[(long long)k * np + j] * v; vv += v * v; }
+        s = warp_sum(s); vv = warp_sum(vv);
+        __syncwarp();
+        if (lane == 0) { lam[k] = s / vv; jb.A[(long long)k * np + k] = 1.0 / sqrt(vv); } /* lambda = v·A0 v / v·v; the scale of row k for the gather */
     }
 }
 /* ascending order by rank (stable on ties); row k of the output = k-th eigenvector (without the padding) */
@@ -1540,7 +1549,7 @@ __global__ void __launch_bounds__(256) eig_gather_kernel(const EigJob* __restric
     const long long tot = (long long)n * n;
     for (long long e = blockIdx.x * 256ll + threadIdx.x; e < tot; e += (long long)gridDim.x * 256) {
         const int i = (int)(e / n), j = (int)(e % n);
-        jb.outA[(long long)rank_of[i] * n + j] = jb.VT[(long long)i * np + j];
+        jb.outA[(long long)rank_of[i] * n + j] = jb.VT[(long long)i * np + j] * jb.A[(long long)i * np + i];
     }
 }
 
