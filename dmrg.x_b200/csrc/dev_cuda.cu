@@ -1301,20 +1301,21 @@ __device__ __forceinline__ int eig_find(const int* __restrict__ prefix, int njob
     return lo;
 }
 
-__global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner) {
+constexpr int ESUB_THREADS = 1024; /* the sub-problem is latency-bound (three barriers per rotation round): all the threads an SM has */
+__global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner) {
     extern __shared__ double jsm[];
     double* A = jsm;                 /* [64][65] */
     double* V = jsm + ET * JAC_LD;   /* rotation, columns = eigenvectors */
     __shared__ double cs[ET / 2][2];
     __shared__ int pq[ET / 2][2];
-    __shared__ double red[JAC_THREADS / 32];
+    __shared__ double red[ESUB_THREADS / 32];
     __shared__ double offsh;
     int k;
     const EigJob jb = jobs[eig_find(prefix, njobs, blockIdx.x, k)];
     const int tid = threadIdx.x, np = jb.np;
     int I, J;
     eig_pair(jb.nb, round % (jb.nb - 1), k, I, J);
-    for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+    for (int e = tid; e < ET * ET; e += ESUB_THREADS) {
         const int i = e >> 6, j = e & 63;
         const int gi = (i < EB ? I * EB + i : J * EB + i - EB), gj = (j < EB ? I * EB + j : J * EB + j - EB);
         A[i * JAC_LD + j] = jb.A[(long long)gi * np + gj];
@@ -1329,7 +1330,7 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
     double off_entry = 0.0;
     for (int sweep = 0; sweep < max_inner; ++sweep) {
         double off = 0.0;
-        for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+        for (int e = tid; e < ET * ET; e += ESUB_THREADS) {
             const int i = e >> 6, j = e & 63;
             const double a = A[i * JAC_LD + j];
             if (i != j) off += a * a;
@@ -1337,7 +1338,7 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
         off = warp_sum(off);
         if ((tid & 31) == 0) red[tid >> 5] = off;
         __syncthreads();
-        if (tid == 0) { double o = 0; for (int w = 0; w < JAC_THREADS / 32; ++w) o += red[w]; offsh = o; }
+        if (tid == 0) { double o = 0; for (int w = 0; w < ESUB_THREADS / 32; ++w) o += red[w]; offsh = o; }
         __syncthreads();
         if (sweep == 0) off_entry = offsh;
         if (offsh <= thr) break;
@@ -1349,37 +1350,44 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
                 const int p = a < b ? a : b, q = a < b ? b : a;
                 double c = 1.0, sn = 0.0;
                 const double apq = A[p * JAC_LD + q];
-                /* the rotation with |angle| <= pi/4 that zeroes a_pq, with two dependent special functions instead of five
-                   (a division and a square root cost ~300 cycles each in FP64 and this step is serial):
-                   d = a_qq - a_pp, b = 2 a_pq, h = hypot(d, b):  c^2 = (h + |d|) / 2h,  s = sgn(d) b / (2 h c) */
+                /* the rotation with |angle| <= pi/4 that zeroes a_pq, with TWO dependent reciprocal square roots and no division
+                   (this step is serial: every special function is latency on the critical path of the whole solver):
+                   d = a_qq - a_pp, b = 2 a_pq, h = hypot(d, b):  c^2 = (h + |d|) / 2h,  c = c^2 / sqrt(c^2),  s = sgn(d) b / (2 h c);
+                   c^2 + s^2 = 1 holds to round-off by construction */
                 const double d = A[q * JAC_LD + q] - A[p * JAC_LD + p], b2 = 2.0 * apq;
                 const double hh = d * d + b2 * b2;
                 if (apq != 0.0 && hh > 1e-290) {
                     const double rh = rsqrt(hh);
                     const double c2 = 0.5 + 0.5 * fabs(d) * rh;
-                    c = sqrt(c2);
-                    sn = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * rsqrt(c2);
+                    const double rc = rsqrt(c2);
+                    c = c2 * rc;
+                    sn = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * rc;
                 }
                 pq[tid][0] = p; pq[tid][1] = q;
                 cs[tid][0] = c; cs[tid][1] = sn;
             }
             __syncthreads();
-            for (int e = tid; e < (ET / 2) * ET; e += JAC_THREADS) { /* columns p, q of A and of V */
-                const int kk = e >> 6, i = e & 63;
-                const int p = pq[kk][0], q = pq[kk][1];
-                const double c = cs[kk][0], sn = cs[kk][1];
-                const double xx = A[i * JAC_LD + p], yy = A[i * JAC_LD + q];
-                A[i * JAC_LD + p] = c * xx - sn * yy; A[i * JAC_LD + q] = sn * xx + c * yy;
-                const double vx = V[i * JAC_LD + p], vy = V[i * JAC_LD + q];
-                V[i * JAC_LD + p] = c * vx - sn * vy; V[i * JAC_LD + q] = sn * vx + c * vy;
-            }
-            __syncthreads();
-            for (int e = tid; e < (ET / 2) * ET; e += JAC_THREADS) { /* rows p, q of A */
-                const int kk = e >> 6, j = e & 63;
-                const int p = pq[kk][0], q = pq[kk][1];
-                const double c = cs[kk][0], sn = cs[kk][1];
-                const double xx = A[p * JAC_LD + j], yy = A[q * JAC_LD + j];
-                A[p * JAC_LD + j] = c * xx - sn * yy; A[q * JAC_LD + j] = sn * xx + c * yy;
+            /* A <- J^T A J and V <- V J in ONE phase: the 2x2 block {p1,q1} x {p2,q2} of A transforms on its own (one thread per
+               block, 32 x 32 blocks), and so does every row of the column pair {p,q} of V — two barriers per round, not three */
+            {
+                const int k1 = tid >> 5, k2 = tid & 31;
+                const int p1 = pq[k1][0], q1 = pq[k1][1], p2 = pq[k2][0], q2 = pq[k2][1];
+                const double c1 = cs[k1][0], s1 = cs[k1][1], c2 = cs[k2][0], s2 = cs[k2][1];
+                const double a11 = A[p1 * JAC_LD + p2], a12 = A[p1 * JAC_LD + q2], a21 = A[q1 * JAC_LD + p2], a22 = A[q1 * JAC_LD + q2];
+                /* columns: [x y] <- [c x - s y, s x + c y] */
+                const double b11 = c2 * a11 - s2 * a12, b12 = s2 * a11 + c2 * a12;
+                const double b21 = c2 * a21 - s2 * a22, b22 = s2 * a21 + c2 * a22;
+                /* rows: same with (c1, s1) */
+                A[p1 * JAC_LD + p2] = c1 * b11 - s1 * b21; A[q1 * JAC_LD + p2] = s1 * b11 + c1 * b21;
+                A[p1 * JAC_LD + q2] = c1 * b12 - s1 * b22; A[q1 * JAC_LD + q2] = s1 * b12 + c1 * b22;
+#pragma unroll
+                for (int e = tid; e < (ET / 2) * ET; e += ESUB_THREADS) {
+                    const int kk = e >> 6, i = e & 63;
+                    const int p = pq[kk][0], q = pq[kk][1];
+                    const double c = cs[kk][0], sn = cs[kk][1];
+                    const double vx = V[i * JAC_LD + p], vy = V[i * JAC_LD + q];
+                    V[i * JAC_LD + p] = c * vx - sn * vy; V[i * JAC_LD + q] = sn * vx + c * vy;
+                }
             }
             __syncthreads();
         }
@@ -1415,7 +1423,7 @@ __global__ void __launch_bounds__(JAC_THREADS) eig_sub_kernel(const EigJob* __re
     if (tid == 0 && rotated) atomicMax((unsigned long long*)jb.maxoff, (unsigned long long)__double_as_longlong(off_entry));
     if (!changed) return;
     double* Q = jb.Q + (long long)k * ET * ET;
-    for (int e = tid; e < ET * ET; e += JAC_THREADS) {
+    for (int e = tid; e < ET * ET; e += ESUB_THREADS) {
         const int i = e >> 6, j = e & 63;
         const int ri = rank_of[i], rj = rank_of[j];
         Q[i * ET + rj] = V[i * JAC_LD + j];
@@ -1646,7 +1654,12 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     LAUNCH_CHECK();
     eig_init_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs);
     LAUNCH_CHECK();
+    /* inner cyclic sweeps per sub-problem: two while the matrix is far from diagonal, one once the sweeps are in their
+       convergent phase (tunable for experiments) */
     static const int max_inner = getenv("DMRGX_JAC_INNER") ? atoi(getenv("DMRGX_JAC_INNER")) : 2;
+    static const int late_inner = getenv("DMRGX_JAC_INNER_LATE") ? atoi(getenv("DMRGX_JAC_INNER_LATE")) : 2;
+    static const int late_from = getenv("DMRGX_JAC_LATE_FROM") ? atoi(getenv("DMRGX_JAC_LATE_FROM")) : 6;
+    int sweeps_done = 0;
     /* live jobs are a prefix-compacted copy of the job list (largest first); tables re-uploaded when a matrix finishes */
     std::vector<int> live((size_t)nj);
     for (int q = 0; q < nj; ++q) live[(size_t)q] = q;
@@ -1676,11 +1689,12 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables are reused below */
         /* one sweep of the largest live matrix (smaller ones complete at least one sweep of their own in the same rounds) */
         for (int rr = 0; rr < maxnb - 1; ++rr, ++round) {
-            eig_sub_kernel<<<sub_prefix[nl], JAC_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, max_inner);
+            eig_sub_kernel<<<sub_prefix[nl], ESUB_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, sweeps_done >= late_from ? late_inner : max_inner);
             LAUNCH_CHECK();
             eig_apply_kernel<<<app_prefix[nl], 128, app_smem, st->s>>>(d_live, d_tab + nl + 1, nl, round);
             LAUNCH_CHECK();
         }
+        ++sweeps_done;
         /* which matrices went through the whole sweep without a rotation? */
         for (int q = 0; q < nl; ++q) CUDA_OK(cudaMemcpyAsync(&h_active[(size_t)q], jobs[(size_t)live[(size_t)q]].active, 4, cudaMemcpyDeviceToHost, st->s));
         CUDA_OK(cudaStreamSynchronize(st->s));
