@@ -59,12 +59,10 @@ struct Stream {
     unsigned int* ticket = nullptr; /* "last block finishes the reduction" counter of gs_pass */
     int* info = nullptr;
     int num_sms = 148;
-    std::map<size_t, std::vector<void*>> free_lists; /* caching allocator: size class -> free blocks */
+    struct Arena { char* base = nullptr; size_t size = 0; std::map<size_t, size_t> free; /* offset -> length of the free ranges */ };
+    std::vector<Arena> arenas;   /* what was actually cudaMalloc'ed */
     std::unordered_map<void*, size_t> live;
     size_t bytes_reserved = 0;
-    std::vector<void*> slabs;    /* what was actually cudaMalloc'ed: blocks are carved from slabs and live on the free lists */
-    char* slab_ptr = nullptr;
-    size_t slab_left = 0;
     double malloc_seconds = 0;   /* time spent in cudaMalloc by the caching allocator (DMRGX_TRACE prints it at the end) */
     long long malloc_calls = 0;
     ncclComm_t comm = nullptr;
@@ -108,7 +106,7 @@ void destroy(Stream* st) {
     if (getenv("DMRGX_TRACE"))
         fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved\n", st->malloc_calls, st->malloc_seconds, st->bytes_reserved / 1e9);
     if (st->comm) comm_destroy_(st);
-    for (void* q : st->slabs) cudaFree(q);
+    for (auto& ar : st->arenas) cudaFree(ar.base);
     cudaFree(st->partials);
     cudaFree(st->ticket);
     cudaFree(st->info);
@@ -119,59 +117,76 @@ int device_of(Stream* st) { return st->device; }
 void make_current(Stream* st) { cudaSetDevice(st->device); }
 void* raw_stream(Stream* st) { return (void*)st->s; }
 
-/* Caching allocator.  A DMRG sweep frees and allocates panels of slowly varying sizes every step; handing each one
-   back to the driver (cudaFreeAsync) let the pool fragment and re-map, which showed up as 200-700 ms stalls inside single
-   steps.  Blocks are rounded up to one of four geometric size classes per octave and kept on per-class free lists for
-   the life of the context.  Everything is ordered on the one stream of the context, so a freed block can be handed out
+/* Device memory: a stream-ordered heap.  A DMRG sweep frees and allocates panels of slowly varying sizes every step; handing
+   each one back to the driver (cudaFreeAsync) let the pool fragment and re-map (200-700 ms stalls inside single steps), and
+   round 1's size-class free lists reserved 65 GB for a 12x6 m = 2048 run once the eigensolver workspaces joined the mix
+   (profiles/r2_eigensolver.md).  Now: arenas of >= 1 GiB from cudaMalloc, inside them a classic best-fit heap with splitting
+   and coalescing of free ranges.  Everything is ordered on the one stream of the context, so a freed range can be handed out
    again immediately: its new user is queued behind its old one. */
-static size_t size_class(size_t bytes) {
-    if (bytes <= 512) return 512;
-    size_t p = 512;
-    while (p * 2 <= bytes) p *= 2;            /* p <= bytes < 2p */
-    const size_t q = p / 4;
-    return p + ((bytes - p + q - 1) / q) * q;  /* p, 1.25p, 1.5p, 1.75p, 2p */
-}
 void* malloc_bytes(Stream* st, size_t bytes) {
-    const size_t cls = size_class(bytes);
-    /* best fit among the cached blocks of this class or up to twice as large: sizes drift from step to step in a sweep, and
-       a cudaMalloc (milliseconds, device-wide synchronisation) per new class showed up as the jitter of the rotation phase */
-    for (auto f = st->free_lists.lower_bound(cls); f != st->free_lists.end() && f->first <= 2 * cls; ++f) {
-        if (f->second.empty()) continue;
-        void* p = f->second.back();
-        f->second.pop_back();
-        st->live[p] = f->first;
-        return p;
-    }
-    /* a new block: carved from the current slab (1 GiB, or the block itself when larger); cudaMalloc is called once per slab —
-       1227 calls and 2 s of a 10 s run went into it when every new block was its own cudaMalloc */
-    constexpr size_t SLAB = (size_t)1 << 30;
-    const size_t need = (cls + 255) & ~(size_t)255;
-    if (st->slab_left < need) {
-        const size_t sz = std::max(SLAB, need);
+    const size_t need = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        /* best fit over the free ranges of all arenas */
+        Stream::Arena* best_a = nullptr;
+        std::map<size_t, size_t>::iterator best;
+        size_t best_len = ~(size_t)0;
+        for (auto& ar : st->arenas)
+            for (auto f = ar.free.begin(); f != ar.free.end(); ++f)
+                if (f->second >= need && f->second < best_len) { best_a = &ar; best = f; best_len = f->second; if (best_len == need) break; }
+        if (best_a) {
+            const size_t off = best->first, len = best->second;
+            best_a->free.erase(best);
+            if (len > need) best_a->free[off + need] = len - need;
+            void* p = best_a->base + off;
+            st->live[p] = need;
+            return p;
+        }
+        if (attempt == 1) break;
+        /* a new arena: 1 GiB, or the request rounded up to 256 MiB when larger */
+        constexpr size_t SLAB = (size_t)1 << 30, GRAIN = (size_t)256 << 20;
+        const size_t sz = std::max(SLAB, (need + GRAIN - 1) / GRAIN * GRAIN);
         void* slab = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMalloc(&slab, sz);
-        if (e != cudaSuccess && sz > need) { cudaGetLastError(); e = cudaMalloc(&slab, need); if (e == cudaSuccess) { st->slabs.push_back(slab); st->bytes_reserved += need; st->live[slab] = cls; return slab; } }
+        if (e != cudaSuccess) {
+            /* out of memory: give wholly free arenas back to the driver and try once more (with just what is needed) */
+            cudaGetLastError();
+            CUDA_OK(cudaStreamSynchronize(st->s));
+            for (size_t i = 0; i < st->arenas.size();) {
+                Stream::Arena& ar = st->arenas[i];
+                if (ar.free.size() == 1 && ar.free.begin()->second == ar.size) { cudaFree(ar.base); st->bytes_reserved -= ar.size; st->arenas.erase(st->arenas.begin() + (long)i); }
+                else ++i;
+            }
+            e = cudaMalloc(&slab, need);
+            if (e == cudaSuccess) { Stream::Arena ar; ar.base = (char*)slab; ar.size = need; ar.free[0] = need; st->arenas.push_back(ar); st->bytes_reserved += need; }
+        } else {
+            Stream::Arena ar; ar.base = (char*)slab; ar.size = sz; ar.free[0] = sz;
+            st->arenas.push_back(ar); st->bytes_reserved += sz;
+        }
         st->malloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         st->malloc_calls++;
         CUDA_OK(e);
-        st->slabs.push_back(slab);
-        st->slab_ptr = (char*)slab;
-        st->slab_left = sz;
-        st->bytes_reserved += sz;
     }
-    void* p = st->slab_ptr;
-    st->slab_ptr += need;
-    st->slab_left -= need;
-    st->live[p] = cls;
-    return p;
+    throw std::runtime_error("device allocator: no room after growing the heap");
 }
 void free_bytes(Stream* st, void* p) {
     if (!p) return;
     auto f = st->live.find(p);
     if (f == st->live.end()) return;
-    st->free_lists[f->second].push_back(p);
+    size_t len = f->second;
     st->live.erase(f);
+    for (auto& ar : st->arenas) {
+        if ((char*)p < ar.base || (char*)p >= ar.base + ar.size) continue;
+        size_t off = (size_t)((char*)p - ar.base);
+        auto nx = ar.free.lower_bound(off);
+        if (nx != ar.free.end() && off + len == nx->first) { len += nx->second; nx = ar.free.erase(nx); } /* merge with the next range */
+        if (nx != ar.free.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) { pv->second += len; return; }                             /* ... and the previous one */
+        }
+        ar.free[off] = len;
+        return;
+    }
 }
 void* malloc_pinned(size_t bytes) { void* p = nullptr; CUDA_OK(cudaMallocHost(&p, bytes ? bytes : 8)); return p; }
 void free_pinned(void* p) { if (p) cudaFreeHost(p); }
