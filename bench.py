@@ -458,7 +458,8 @@ def main():
                           "only %.0f MB on a rank" % (per_rank_bytes / 1e6)) if flush_l2 else
                          ("no flush needed: one apply streams through %.0f MB on this rank (V workspace + pre-summed factors + psi, plus %.0f MB of "
                           "operator panels), more than twice the 126 MB L2" % (st["workspace_bytes"] / 1e6, (st["alg_bytes"] - 16 * n) / 1e6)),
-                   "parallelism": ("superblock rows sharded over %d GPUs (cuts %s), NCCL all-gather of psi per apply" % (world, cuts.tolist()))
+                   "parallelism": ("superblock rows sharded over %d GPUs (cuts %s), NCCL sector-halo exchange of psi per apply: rank 0 receives %.1f MB "
+                                   "(an all-gather would bring %.1f MB)" % ((world, cuts.tolist()) + tuple(v / 1e6 for v in H.halo_bytes())))
                    if world > 1 else "single"},
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * (re_ - rb), "d2h_bytes_per_step": 8 * (re_ - rb), "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),

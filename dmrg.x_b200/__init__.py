@@ -357,6 +357,12 @@ class HShell:
         _chk(lib().dmrgx_hshell_row_range(self.h, C.byref(b), C.byref(e), _p(cuts)))
         return b.value, e.value, cuts
 
+    def halo_bytes(self):
+        """(bytes of psi this rank receives per sharded apply, what an all-gather would bring)"""
+        a, b = C.c_double(), C.c_double()
+        _chk(lib().dmrgx_hshell_halo_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def MatMult_sharded(self, x, y):
         """distributed MatMult: x holds this rank's rows on entry (full-length buffer), is all-gathered in place, then this
         rank's rows of y are computed"""

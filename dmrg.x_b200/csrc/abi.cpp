@@ -153,6 +153,12 @@ int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, cons
 }
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y) { return guard([&] { hshell_apply(H(h), d_x, d_y); }); }
 int dmrgx_hshell_apply_sharded(dmrgx_hshell h, double* d_x, double* d_y) { return guard([&] { hshell_apply_sharded(H(h), d_x, d_y); }); }
+int dmrgx_hshell_halo_bytes(dmrgx_hshell h, double* halo, double* allgather) {
+    HShell* s = H(h);
+    if (halo) *halo = 8.0 * (double)s->halo_recv_elems;
+    if (allgather) *allgather = 8.0 * (double)(s->n - (s->row_end - s->row_begin)) * (s->ctx->world > 1 ? 1.0 : 0.0);
+    return 0;
+}
 int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmrgx_int* cuts) {
     HShell* s = H(h);
     if (begin) *begin = s->row_begin;

@@ -133,6 +133,11 @@ struct Plan {
     long long scratch_elems = 0;
     /* when > 0, emit_cells cuts chains whose cost (sum of K) times tile area exceeds this many multiply-adds */
     double split_item_cost = 0;
+    /* launch order: items are sorted by (phase, cost descending).  Stage 2 of the shell sets phase = index of the chain part,
+       so that the CTAs resident at any time work on the same range of left-operator groups: their V and right-factor
+       panels (a fraction of the 270 + 93 MB at 12x6 m = 2048) then fit in L2 together instead of being re-read. */
+    std::vector<int> item_phase;
+    bool phase_order = false;
     BufRef d_items, d_segs, d_reduces, scratch;
     void upload(Ctx* ctx);
     void run(Ctx* ctx, const double* x = nullptr, double* y = nullptr) const;
@@ -160,6 +165,11 @@ struct HShell {
     /* superblock rows this rank computes ([0,n) on one GPU) and the ownership table of all ranks (world+1 entries) */
     long long row_begin = 0, row_end = 0;
     std::vector<long long> row_cuts;
+    /* sector halo of the sharded apply: the point-to-point transfers that bring every rank the X_q panels its
+       tiles read and nothing else — the same list on every rank */
+    std::vector<int> halo_from, halo_to;
+    std::vector<long long> halo_off, halo_cnt;
+    long long halo_recv_elems = 0;   /* what this rank receives per apply */
     Plan stage1, stage2;
     std::unique_ptr<SparsePlan> sparse; /* when set, the apply is one spmm launch and stage1 / stage2 are empty */
     BufRef work;                 /* V panels of stage 1 */

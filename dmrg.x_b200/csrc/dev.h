@@ -90,6 +90,9 @@ int comm_world(Stream*);
 void allreduce_sum(Stream*, double* d_buf, long long n); /* in place */
 /* in place: rank r owns d_buf[offsets[r] .. offsets[r+1]) and receives all other ranges */
 void allgatherv(Stream*, double* d_buf, const long long* offsets);
+/* sector-halo exchange: transfer i moves d_buf[off[i] .. off[i]+cnt[i]) from rank from[i] to rank to[i] (same place in the
+   receiver's buffer); the same list on every rank, one NCCL group of point-to-point transfers */
+void exchange_ranges(Stream*, double* d_buf, int n, const int* from, const int* to, const long long* off, const long long* cnt);
 /* a batch of broadcasts, root[i] sends d_ptr[i][0..count[i]) to everybody (one NCCL group) */
 void bcast_batch(Stream*, int n, double* const* d_ptr, const long long* count, const int* root);
 

@@ -1130,6 +1130,16 @@ void allgatherv(Stream* st, double* d_buf, const long long* off) {
     }
     NCCL_OK(nccl().GroupEnd());
 }
+void exchange_ranges(Stream* st, double* d_buf, int n, const int* from, const int* to, const long long* off, const long long* cnt) {
+    if (st->world <= 1 || n <= 0) return;
+    NCCL_OK(nccl().GroupStart());
+    for (int i = 0; i < n; ++i) {
+        if (cnt[i] <= 0 || from[i] == to[i]) continue;
+        if (from[i] == st->rank) NCCL_OK(nccl().Send(d_buf + off[i], (size_t)cnt[i], ncclDouble, to[i], st->comm, st->s));
+        if (to[i] == st->rank) NCCL_OK(nccl().Recv(d_buf + off[i], (size_t)cnt[i], ncclDouble, from[i], st->comm, st->s));
+    }
+    NCCL_OK(nccl().GroupEnd());
+}
 void bcast_batch(Stream* st, int n, double* const* d_ptr, const long long* count, const int* root) {
     if (st->world <= 1 || n <= 0) return;
     NCCL_OK(nccl().GroupStart());

@@ -531,6 +531,7 @@ static HShell* build_shell(const Kron* kron, const std::vector<Group>& groups, i
         const double chunks_total = probe.flops / (2.0 * 64 * 64 * 16);
         const double target_items = tgt ? 444.0 * atof(tgt) : std::min(3.0 * 444.0, std::max(444.0, chunks_total / 40.0));
         if (probe.flops > 0 && (double)probe.items.size() < target_items) H->stage2.split_item_cost = 0.5 * probe.flops / target_items;
+        H->stage2.phase_order = getenv("DMRGX_NO_PHASE_ORDER") == nullptr;
     }
     for (int p = 0; p < np; ++p) {
         const int nLp = lr1[p] - lr0[p], nRp = SR.size[kron->pairs[p].ir];
@@ -588,6 +589,38 @@ static std::vector<long long> shard_rows(const Kron* kron, const std::vector<Gro
     return cuts;
 }
 
+/* The sector halo (the reference gathers ALL of psi on every rank, src/DMRGKron.cpp:1833-1834): a rank's tiles read
+   only the pairs q = (IL + sA, IR + sB) of its own pairs' terms — Sz shifts of -1, 0, +1, i.e. neighbouring sector pairs.
+   Every rank derives the needs of every rank from the ownership table, so all ranks hold the same transfer list. */
+static void plan_halo(HShell* H, const Kron* kron, const std::vector<Group>& groups, const std::vector<long long>& cuts) {
+    const Sectors &SL = kron->L->sec, &SR = kron->R->sec;
+    const int np = (int)kron->pairs.size(), world = (int)cuts.size() - 1, me = kron->ctx->rank;
+    for (int r = 0; r < world; ++r) {
+        std::vector<char> need(np, 0);
+        for (int p = 0; p < np; ++p) {
+            if (std::min(cuts[r + 1], kron->off[p + 1]) <= std::max(cuts[r], kron->off[p])) continue; /* rank r owns no row of pair p */
+            for (const Group& G : groups) {
+                const int jl = kron->pairs[p].il + G.sA, jr = kron->pairs[p].ir + G.sB;
+                if (jl < 0 || jl >= SL.nsec() || jr < 0 || jr >= SR.nsec()) continue;
+                const int q = kron->find(jl, jr);
+                if (q >= 0 && G.A) need[q] = 1; /* an identity left factor reads the rank's own rows only */
+            }
+        }
+        for (int q = 0; q < np; ++q) {
+            if (!need[q]) continue;
+            for (int s = 0; s < world; ++s) {
+                if (s == r) continue;
+                const long long a = std::max(kron->off[q], cuts[s]), b = std::min(kron->off[q + 1], cuts[s + 1]);
+                if (b <= a) continue;
+                /* merge with the previous transfer of the same (s, r) when contiguous */
+                if (!H->halo_from.empty() && H->halo_from.back() == s && H->halo_to.back() == r && H->halo_off.back() + H->halo_cnt.back() == a) H->halo_cnt.back() += b - a;
+                else { H->halo_from.push_back(s); H->halo_to.push_back(r); H->halo_off.push_back(a); H->halo_cnt.push_back(b - a); }
+            }
+        }
+    }
+    for (size_t i = 0; i < H->halo_to.size(); ++i) if (H->halo_to[i] == me) H->halo_recv_elems += H->halo_cnt[i];
+}
+
 static HShell* build_sharded(const Kron* kron, const std::vector<Group>& groups, int nterms) {
     Ctx* ctx = kron->ctx;
     if (ctx->world <= 1) {
@@ -601,6 +634,7 @@ static HShell* build_sharded(const Kron* kron, const std::vector<Group>& groups,
     HShell* H = build_shell(kron, groups, nterms, cuts[ctx->rank], cuts[ctx->rank + 1]);
     H->row_cuts = cuts;
     H->alg_bytes_global = gb; H->alg_flops_global = gf;
+    plan_halo(H, kron, groups, cuts);
     return H;
 }
 
@@ -757,7 +791,10 @@ void hshell_apply(HShell* H, const double* d_x, double* d_y) {
    the exchange step of the path (the VecScatter-to-all of src/DMRGKron.cpp:1833-1834) is an in-place all-gather over
    NVLink, after which this rank computes its own rows of y. */
 void hshell_apply_sharded(HShell* H, double* d_x, double* d_y) {
-    if (H->ctx->world > 1) dev::allgatherv(H->ctx->st, d_x, H->row_cuts.data());
+    if (H->ctx->world > 1) {
+        if (getenv("DMRGX_FULL_GATHER")) dev::allgatherv(H->ctx->st, d_x, H->row_cuts.data()); /* experiment hook: the reference's all-gather */
+        else dev::exchange_ranges(H->ctx->st, d_x, (int)H->halo_from.size(), H->halo_from.data(), H->halo_to.data(), H->halo_off.data(), H->halo_cnt.data());
+    }
     hshell_apply(H, d_x, d_y);
 }
 

@@ -38,7 +38,11 @@ void Plan::upload(Ctx* ctx) {
     }
     std::vector<size_t> ord(items.size());
     for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
-    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+    const bool by_phase = phase_order && item_phase.size() == items.size();
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+        if (by_phase && item_phase[a] != item_phase[b]) return item_phase[a] < item_phase[b];
+        return cost[a] > cost[b];
+    });
     std::vector<dev::WorkItem> sorted(items.size());
     for (size_t i = 0; i < ord.size(); ++i) sorted[i] = items[ord[i]];
     items.swap(sorted);
@@ -161,6 +165,7 @@ void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Nc
                         it.C = dst; it.ldc = ldc; it.c_in_y = c_in_y ? 1 : 0;
                         it.seg_begin = seg_begin; it.seg_end = seg_end;
                         plan.items.push_back(it);
+                        plan.item_phase.push_back(0);
                     } else {
                         dev::ReduceItem ri;
                         std::memset(&ri, 0, sizeof ri);
@@ -172,6 +177,7 @@ void emit_cells(Plan& plan, double* C, bool c_in_y, long long ldc, int R, int Nc
                             it.ldc = tn; it.c_in_y = 2;
                             it.seg_begin = part_begin[pp]; it.seg_end = part_begin[pp + 1];
                             plan.items.push_back(it);
+                            plan.item_phase.push_back(pp);
                         }
                         plan.scratch_elems += (long long)nparts * tm * tn;
                     }

@@ -106,9 +106,13 @@ int dmrgx_hshell_create_product(dmrgx_kron k, dmrgx_int nl, const int* lop, cons
 /* MatMult_KronSumShell(A, x, y): src/DMRGKron.cpp:1827-1869.  Device pointers, length NumStates(). */
 int dmrgx_hshell_apply(dmrgx_hshell h, const double* d_x, double* d_y);
 /* The distributed form of the same callback.  d_x: full-length device buffer in which this rank's rows are valid on entry;
-   the VecScatter-to-all of src/DMRGKron.cpp:1833-1834 becomes an in-place NCCL all-gather, then this rank's rows of d_y
-   (also a full-length buffer) are computed.  On one GPU identical to dmrgx_hshell_apply. */
+   the VecScatter-to-all of src/DMRGKron.cpp:1833-1834 becomes an in-place sector-halo exchange over NCCL (only the sector pairs
+   this rank's rows couple to arrive; the rest of d_x is left as it was), then this rank's rows of d_y (also a full-length
+   buffer) are computed.  On one GPU identical to dmrgx_hshell_apply. */
 int dmrgx_hshell_apply_sharded(dmrgx_hshell h, double* d_x, double* d_y);
+/* bytes of psi this rank RECEIVES per sharded apply (the sector halo: only the X_q panels its tiles read) and what the reference's
+   VecScatter-to-all (src/DMRGKron.cpp:1833-1834) would bring it */
+int dmrgx_hshell_halo_bytes(dmrgx_hshell h, double* halo_recv_bytes, double* allgather_recv_bytes);
 /* rows [begin,end) this rank owns; cuts (optional, world+1 entries) = the ownership table of all ranks */
 int dmrgx_hshell_row_range(dmrgx_hshell h, dmrgx_int* begin, dmrgx_int* end, dmrgx_int* cuts);
 /* profiling aids: run only stage 1 (V = A·X panels) or stage 2 (Y = Σ V·Bᵀ) of an apply, and their useful flops */

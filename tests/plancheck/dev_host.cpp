@@ -235,6 +235,17 @@ void allgatherv(Stream*, double* buf, const long long* off) {
     if (g_world <= 1) return;
     for (int r = 0; r < g_world; ++r) if (off[r + 1] > off[r]) g_bcast(buf + off[r], off[r + 1] - off[r], r);
 }
+/* delivered to the named receiver ONLY (the other ranks take the broadcast into a scratch buffer): a halo the planner forgot
+   stays missing and the parity tests see it */
+void exchange_ranges(Stream*, double* buf, int n, const int* from, const int* to, const long long* off, const long long* cnt) {
+    if (g_world <= 1) return;
+    std::vector<double> tmp;
+    for (int i = 0; i < n; ++i) {
+        if (cnt[i] <= 0 || from[i] == to[i]) continue;
+        if (g_rank == from[i] || g_rank == to[i]) g_bcast(buf + off[i], cnt[i], from[i]);
+        else { tmp.resize((size_t)cnt[i]); g_bcast(tmp.data(), cnt[i], from[i]); }
+    }
+}
 void bcast_batch(Stream*, int n, double* const* ptr, const long long* count, const int* root) {
     if (g_world <= 1) return;
     for (int i = 0; i < n; ++i) if (count[i] > 0) g_bcast(ptr[i], count[i], root[i]);
