@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="j1j2_12x6")
-    ap.add_argument("--m", type=int, default=2048)
+    ap.add_argument("--m", "--mstates", dest="m", type=int, default=2048, help="kept states of the synthetic blocks (use --mstates under torchrun: its parser "
+                    "takes a bare --m for one of its own options)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison on a row sample")
