@@ -38,6 +38,9 @@ def sector_sizes(m, nsites, sigma=2.5):
     qn, sz = qn[keep[0]:keep[-1] + 1], sz[keep[0]:keep[-1] + 1]
     c = len(sz) // 2
     sz[c] += m - sz.sum()
+    rnd = int(os.environ.get("DMRGX_SECTOR_ROUND", "0"))   # experiment hook: sector sizes in multiples of `rnd` (no ragged tiles)
+    if rnd > 1:
+        sz = np.maximum(rnd, (sz + rnd // 2) // rnd * rnd)
     order = np.argsort(-qn)
     return qn[order].tolist(), sz[order].tolist()
 

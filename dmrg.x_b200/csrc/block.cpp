@@ -391,6 +391,97 @@ Contribution add_tile_contribution(const Tile& t, int r0, int c0, double coef) {
     return c;
 }
 
+/* KronEye_Explicit for a GENERAL right block (several sites, sectors of any size): src/DMRGKron.cpp:459-615 with the index
+   maps of :323-437.  The DMRG loop never calls this form (it always adds one site, handled on the device below); it exists so
+   that the reference's own operator-level golden case (tests/UnitTests_DMRGKron.cpp:39-252, TestKron01) can be replayed on
+   the product.  The Kronecker products are assembled on the host from the operators' CSR form — setup code, like the
+   reference's MatSetValues assembly — and handed to block_set_operator, which cuts them into device tiles. */
+static Block* block_enlarge_general(const Block* L, const Block* R, const std::vector<Term>& terms) {
+    Ctx* ctx = L->ctx;
+    const Sectors &SL = L->sec, &SR = R->sec;
+    struct KB { double qn; int il, ir, size; };
+    std::vector<KB> kb;
+    for (int il = 0; il < SL.nsec(); ++il)
+        for (int ir = 0; ir < SR.nsec(); ++ir) kb.push_back({SL.qn[il] + SR.qn[ir], il, ir, SL.size[il] * SR.size[ir]});
+    std::stable_sort(kb.begin(), kb.end(), [](const KB& a, const KB& b) { return a.qn > b.qn; }); /* include/DMRGKron.hpp:147-158 */
+    const int np = (int)kb.size();
+    std::vector<long long> kboff(np + 1, 0);
+    std::map<std::pair<int, int>, int> kmap;
+    std::vector<double> qn_list;
+    std::vector<long long> qn_size;
+    for (int p = 0; p < np; ++p) {
+        kboff[p + 1] = kboff[p] + kb[p].size;
+        kmap[{kb[p].il, kb[p].ir}] = p;
+        if (qn_list.empty() || kb[p].qn < qn_list.back()) { qn_list.push_back(kb[p].qn); qn_size.push_back(kb[p].size); }
+        else qn_size.back() += kb[p].size; /* equal-QN blocks merge into one sector (src/DMRGKron.cpp:560-574) */
+    }
+    const int nsL = L->nsites, nsR = R->nsites, nsO = nsL + nsR;
+    const long long N = kboff[np];
+    std::unique_ptr<Block> out(block_from_csr_begin(ctx, nsO, qn_list, qn_size));
+    /* state (left global index gl, right global index gr) -> row of the enlarged block: offset of its pair + l*n_R + r */
+    auto idx = [&](int gl, int gr) {
+        const int il = SL.sector_of(gl), ir = SR.sector_of(gr);
+        return kboff[kmap.at({il, ir})] + (long long)(gl - SL.off[il]) * SR.size[ir] + (gr - SR.off[ir]);
+    };
+    struct Csr { std::vector<long long> rp, ci; std::vector<double> vv; };
+    auto fetch = [&](const Block* b, int op, int i) { Csr c; block_get_operator(b, op, i, c.rp, c.ci, c.vv); return c; };
+    typedef std::vector<std::map<long long, double>> Rows;
+    auto commit = [&](int optype, int isite, const Rows& rows, double tol) {
+        Csr c;
+        c.rp.assign((size_t)N + 1, 0);
+        for (long long r = 0; r < N; ++r) {
+            for (auto& kv : rows[(size_t)r]) {
+                if (tol > 0 && std::fabs(kv.second) < tol) continue; /* ks_tol filter (src/DMRGKron.cpp:1449-1454) */
+                c.ci.push_back(kv.first); c.vv.push_back(kv.second);
+            }
+            c.rp[(size_t)r + 1] = (long long)c.ci.size();
+        }
+        block_set_operator(out.get(), optype, isite, c.rp.data(), c.ci.data(), c.vv.data());
+    };
+    const int nL = SL.nstates(), nR = SR.nstates();
+    /* rows += coef * (A ⊗ B); A or B == nullptr is the identity */
+    auto add_kron = [&](Rows& rows, const Csr* A, const Csr* B, double coef) {
+        for (int gl = 0; gl < nL; ++gl) {
+            const long long a0 = A ? A->rp[(size_t)gl] : 0, a1 = A ? A->rp[(size_t)gl + 1] : 1;
+            for (long long ea = a0; ea < a1; ++ea) {
+                const int cl = A ? (int)A->ci[(size_t)ea] : gl;
+                const double va = A ? A->vv[(size_t)ea] : 1.0;
+                for (int gr = 0; gr < nR; ++gr) {
+                    const long long b0 = B ? B->rp[(size_t)gr] : 0, b1 = B ? B->rp[(size_t)gr + 1] : 1;
+                    for (long long eb = b0; eb < b1; ++eb) {
+                        const int cr = B ? (int)B->ci[(size_t)eb] : gr;
+                        const double vb = B ? B->vv[(size_t)eb] : 1.0;
+                        rows[(size_t)idx(gl, gr)][idx(cl, cr)] += coef * va * vb;
+                    }
+                }
+            }
+        }
+    };
+    for (int i = 0; i < nsL; ++i)
+        for (int op : {OP_SZ, OP_SP}) { Csr A = fetch(L, op, i); Rows rows((size_t)N); add_kron(rows, &A, nullptr, 1.0); commit(op, i, rows, 0.0); }
+    for (int j = 0; j < nsR; ++j)
+        for (int op : {OP_SZ, OP_SP}) { Csr B = fetch(R, op, j); Rows rows((size_t)N); add_kron(rows, nullptr, &B, 1.0); commit(op, nsL + j, rows, 0.0); }
+    {
+        Rows rows((size_t)N);
+        Csr HL = fetch(L, OP_H, 0), HR = fetch(R, OP_H, 0);
+        add_kron(rows, &HL, nullptr, 1.0);
+        add_kron(rows, nullptr, &HR, 1.0);
+        for (const Term& t : terms) { /* src/DMRGKron.cpp:788-807 */
+            if (t.Isite >= 0 && t.Isite < nsL && t.Jsite >= nsL && t.Jsite < nsO) {
+                if (t.a == 0.0) continue;
+                if (t.Iop < OP_SM || t.Iop > OP_SP || t.Jop < OP_SM || t.Jop > OP_SP) throw Err(ERR_ARG_WRONG, "Incorrect operator type.");
+                Csr A = fetch(L, t.Iop, (int)t.Isite), B = fetch(R, t.Jop, (int)(nsO - 1 - t.Jsite)); /* the right block is mirrored */
+                add_kron(rows, &A, &B, t.a);
+            } else if (t.Isite >= 0 && t.Isite < nsL && t.Jsite >= 0 && t.Jsite < nsL) {
+            } else if (t.Isite >= nsL && t.Isite < nsO && t.Jsite >= nsL && t.Jsite < nsO) {
+            } else throw Err(ERR_GENERIC, "Invalid term: site index out of range");
+        }
+        commit(OP_H, 0, rows, 1.0e-16);
+    }
+    block_check(out.get());
+    return out.release();
+}
+
 /* ------------------------------------------------------------------------------------------------
  *  KronEye_Explicit with a single-site right block (src/DMRGKron.cpp:459-615; index maps :323-437;
  *  enlarged-block H :844-881 + :1340-1477 with the ks_tol filter :1449-1454).
@@ -402,7 +493,7 @@ Block* block_enlarge(const Block* L, const Block* site, const std::vector<Term>&
     const Sectors& SL = L->sec;
     const Sectors& SR = site->sec;
     for (int s : SR.size)
-        if (s != 1) throw Err(ERR_SUP, "block_enlarge: the added block must have one state per sector (a single site)");
+        if (s != 1) return block_enlarge_general(L, site, terms);
     /* KronBlocks_t with all sectors: IL-major, stable sort by descending QN (include/DMRGKron.hpp:147-158) */
     struct KB { double qn; int il, ir, size; };
     std::vector<KB> kb;

@@ -74,8 +74,9 @@ int dmrgx_block_sectors(dmrgx_block blk, double* qn_list, dmrgx_int* qn_size);
 /* CheckOperatorBlocks: src/DMRGBlock.cpp:603-620 */
 int dmrgx_block_check(dmrgx_block blk);
 int dmrgx_block_destroy(dmrgx_block blk);
-/* KronEye_Explicit(Left, AddSite, Terms, BlockOut): src/DMRGKron.cpp:459-615.  `site` must have one state per
-   sector (a single site, which is the only way the reference's DMRG loop calls it). */
+/* KronEye_Explicit(Left, Right, Terms, BlockOut): src/DMRGKron.cpp:459-615.  A right block with one state per sector (a single
+   site: the only way the reference's DMRG loop calls it) is enlarged on the device without moving operator data; a general
+   right block (several sites / wider sectors, e.g. the reference's TestKron01 case) is assembled from the CSR forms. */
 int dmrgx_block_enlarge(dmrgx_block left, dmrgx_block site, dmrgx_int nterms, const double* a, const int* iop, const dmrgx_int* isite,
                         const int* jop, const dmrgx_int* jsite, dmrgx_block* out);
 

@@ -266,3 +266,46 @@ def check_step_fixture(P, ctx, golden_dir):
         assert abs(bt.TruncErr - ref["err"]) <= ENERGY_RTOL * max(abs(ref["err"]), 1e-4)
         ev = np.sort(bt.spectrum()[0])[::-1]
         assert np.abs(ev - np.array(ref["spectrum"])).max() <= 1e-12
+
+
+def check_testkron01_operator_rows(P, ctx, golden_dir):
+    """The reference's only operator-level golden (tests/UnitTests_DMRGKron.cpp:39-252, TestKron01: a 3-site left block with
+    sectors {+.5: 2, -.5: 1} times a 2-site right block with sectors {+1: 1, 0: 2, -1: 1}, matrix values == column indices,
+    tests/UnitTests_Misc.cpp:15-18) replayed on the PRODUCT through the C ABI: all 120 expected rows of the 10 enlarged
+    operators.  A stored 0.0 (the fixture's column 0) is indistinguishable from an absent entry in a device tile, so rows are
+    compared on their non-zero entries."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(golden_dir, "testkron01.json")))
+
+    def block(spec):
+        blk = P.Block.Initialize(ctx, spec["nsites"], spec["qn"], spec["sizes"])
+        n = int(sum(spec["sizes"]))
+        for op, code in (("Sz", P.OpSz), ("Sp", P.OpSp)):
+            for site in range(spec["nsites"]):
+                rows = [[] for _ in range(n)]
+                for r in spec["rows"]:
+                    if r["op"] == op and r["site"] == site:
+                        rows[r["row"]] = list(r["cols"])
+                rowptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+                col = np.array([c for r in rows for c in r], np.int64)
+                blk.set_operator(code, site, rowptr, col, col.astype(float))
+        blk.set_operator(P.OpH, 0, np.zeros(n + 1, np.int64), np.zeros(0, np.int64), np.zeros(0))
+        return blk
+    L, R = block(fx["blocks"]["Left"]), block(fx["blocks"]["Right"])
+    out = P.KronEye_Explicit(L, R, [])
+    assert out.NumSites() == 5 and out.NumStates() == 12 and out.CheckOperatorBlocks() == 0
+    q, s = out.sectors()
+    assert q.tolist() == [1.5, 0.5, -0.5, -1.5] and s.tolist() == [2, 5, 4, 1]
+    ops, seen = {}, 0
+    for e in fx["expected"]:
+        key = (e["op"], e["site"])
+        if key not in ops:
+            ops[key] = out.get_operator(P.OpSz if e["op"] == "Sz" else P.OpSp, e["site"])
+        rowptr, col, val = ops[key]
+        r = e["row"]
+        got = [(int(c), float(v)) for c, v in zip(col[rowptr[r]:rowptr[r + 1]], val[rowptr[r]:rowptr[r + 1]]) if v != 0.0]
+        exp = [(int(c), float(v)) for c, v in zip(e["cols"], e["vals"]) if v != 0.0]
+        assert got == exp, (key, r, got, exp)
+        seen += 1
+    assert len(ops) == 10 and seen == len(fx["expected"]) == 120

@@ -181,6 +181,10 @@ def test_testkron01_kronblocks_golden(P, ctx, golden_dir):
     pc.check_testkron01_kronblocks(P, ctx, golden_dir)
 
 
+def test_testkron01_operator_rows_on_the_product(P, ctx, golden_dir):
+    pc.check_testkron01_operator_rows(P, ctx, golden_dir)
+
+
 def test_frozen_step_fixture(P, ctx, golden_dir):
     pc.check_step_fixture(P, ctx, golden_dir)
 
