@@ -349,13 +349,20 @@ def main():
     sampler.start()
     # the timed region lasts a few milliseconds, nvidia-smi samples every 100 ms: the same applies run (untimed) for 0.4 s
     # before and after it, so that the clocks / throttle reasons reported are those of this load
-    def soak(seconds):
-        t_end = time.time() + seconds
-        while time.time() < t_end:
-            for _ in range(10):
-                apply_fn()
-            torch.cuda.synchronize()
-    soak(0.4)
+    t_probe = time.time()
+    for _ in range(5):
+        apply_fn()
+    torch.cuda.synchronize()
+    est = torch.tensor([(time.time() - t_probe) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)   # the same number of (collective) applies on every rank
+    n_soak = int(min(5000, max(10, 0.4 / max(float(est.item()), 1e-6))))
+
+    def soak():
+        for _ in range(n_soak):
+            apply_fn()
+        torch.cuda.synchronize()
+    soak()
     barrier()
     l0 = P.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,7 +394,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
     launches = P.launch_count() - l0
-    soak(0.4)
+    soak()
     clocks = sampler.stop()
     t_local = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
