@@ -109,7 +109,7 @@ void run_chain(Stream*, const WorkItem* d_items, int nitems, const Segment* d_se
  *  lists of (source row of psi, weight[, right factor]) entries, so that the CTA reaches its psi loads after two dependent
  *  fetches and has the loads of eight rows in flight together.
  * ---------------------------------------------------------------------------------------------- */
-constexpr int SP_ROWS = 8;          /* left rows per CTA */
+constexpr int SP_ROWS = 4;          /* left rows per CTA */
 /* Row programs, slot-major: slot k holds the k-th entry of EACH of the tile's 8 rows, so that a CTA issues the psi loads of
    eight rows at once.  src = element offset in x of the source row of X_q; rows with fewer entries carry w = 0 and a valid src. */
 struct SpASlot { long long src[SP_ROWS]; double w[SP_ROWS]; };   /* identity on the right, source row in L2: acc(r,c) += w_r · x[src_r + c] */

@@ -517,7 +517,7 @@ void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d
 
 /* ================================================================================================
  *  spmm_kernel — the sparse-sector matvec (north_star (a)): un-truncated blocks, every operator factor sparse or the
- *  identity.  One CTA per (sector pair, SP_ROWS consecutive left rows); threads run along the right index and keep all
+ *  identity.  One CTA per (sector pair, SP_ROWS = 4 consecutive left rows); threads run along the right index and keep all
  *  SP_ROWS rows of their (strided) columns in registers, so every access to psi is a coalesced row segment, a right
  *  factor's (column, value) pair is fetched once and used for eight rows, and y is written exactly once.
  *    - the CTA's own rows of X_p (one contiguous range of psi) are staged in shared memory by ONE TMA bulk copy
@@ -559,7 +559,7 @@ __device__ __forceinline__ void sp_stage(T* dst, const T* src, int count, int ti
     for (int i = tid; i < count * (int)(sizeof(T) / 8); i += SP_BD) ((double*)dst)[i] = __ldg((const double*)src + i);
 }
 
-__global__ void __launch_bounds__(SP_BD, 2) spmm_kernel(const SpTile* __restrict__ tiles, const SpASlot* __restrict__ aslots, const SpSSlot* __restrict__ sslots,
+__global__ void __launch_bounds__(SP_BD, 3) spmm_kernel(const SpTile* __restrict__ tiles, const SpASlot* __restrict__ aslots, const SpSSlot* __restrict__ sslots,
                                                        const SpBSlot* __restrict__ bslots, const double* __restrict__ x, double* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ unsigned long long mbar;
