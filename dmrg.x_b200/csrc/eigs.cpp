@@ -90,7 +90,9 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     /* ... and only where a matvec on THIS rank is long enough (>= 10 GFLOP, ~0.4 ms) to hide the host round trip of the test: on
        8 GPUs a sharded matvec of the 12x6 m = 2048 superblock takes 0.35 ms and the per-step synchronisation cost 0.3 ms
        (profiles/r2_multigpu.md) */
-    const bool early_test = early_env ? NG >= atoll(early_env) : (NG >= 50000LL && H->alg_flops >= 1e10);
+    /* (on several GPUs the round trip is dearer still — the NCCL operations of the next step are enqueued by the host after it —
+       so the bar is twenty times higher there) */
+    const bool early_test = early_env ? NG >= atoll(early_env) : (NG >= 50000LL && H->alg_flops >= (dist ? 2e11 : 1e10));
     int nc = ld, k = 0;
     double theta = 0, resid = 0;
     for (long long it = 0; it < max_it; ++it) {
