@@ -68,6 +68,8 @@ struct Stream {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     int spmm_smem = 0;           /* dynamic shared memory spmm_kernel has been configured for on this device */
+    cudaStream_t aux = nullptr;  /* side stream: the small-block eigensolver runs beside the block-Jacobi launches */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 constexpr int RED_BLOCKS = 592; /* 148 SMs × 4 resident CTAs */
@@ -106,6 +108,9 @@ void destroy(Stream* st) {
     if (getenv("DMRGX_TRACE"))
         fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved\n", st->malloc_calls, st->malloc_seconds, st->bytes_reserved / 1e9);
     if (st->comm) comm_destroy_(st);
+    if (st->aux) cudaStreamDestroy(st->aux);
+    if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+    if (st->ev_join) cudaEventDestroy(st->ev_join);
     for (auto& ar : st->arenas) cudaFree(ar.base);
     cudaFree(st->partials);
     cudaFree(st->ticket);
@@ -1293,13 +1298,31 @@ __device__ __forceinline__ void eig_pair(int nb, int r, int k, int& I, int& J) {
     I = a < b ? a : b; J = a < b ? b : a;
 }
 
-__global__ void __launch_bounds__(256) eig_init_kernel(const EigJob* __restrict__ jobs) {
+/* Starting order: the coordinates sorted by DESCENDING diagonal entry.  In a DMRG step the basis of a block is (kept states of
+   the previous step, already ordered by weight) x (site states), so the diagonal of rho is informative and the sorted matrix
+   starts out graded — the form on which the sorted block Jacobi converges fastest.  perm[i] = original coordinate at position i
+   (the rank array of the finish step doubles as scratch for it). */
+__global__ void __launch_bounds__(256) eig_perm_kernel(const EigJob* __restrict__ jobs, int* __restrict__ perm_ws, const int* __restrict__ perm_off, int presort) {
     const EigJob jb = jobs[blockIdx.y];
+    int* perm = perm_ws + perm_off[blockIdx.y];
+    const int n = jb.n;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        if (!presort) { perm[i] = i; continue; }
+        const double di = jb.outA[(long long)i * n + i];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) { const double dj = jb.outA[(long long)j * n + j]; rk += (dj > di || (dj == di && j < i)) ? 1 : 0; }
+        perm[rk] = i;
+    }
+}
+__global__ void __launch_bounds__(256) eig_init_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ perm_ws, const int* __restrict__ perm_off) {
+    const EigJob jb = jobs[blockIdx.y];
+    const int* perm = perm_ws + perm_off[blockIdx.y];
     const long long tot = (long long)jb.np * jb.np;
     for (long long e = blockIdx.x * 256ll + threadIdx.x; e < tot; e += (long long)gridDim.x * 256) {
         const int i = (int)(e / jb.np), j = (int)(e % jb.np);
-        jb.A[e] = (i < jb.n && j < jb.n) ? jb.outA[(long long)i * jb.n + j] : 0.0;
-        jb.VT[e] = i == j ? 1.0 : 0.0;
+        const bool in = i < jb.n && j < jb.n;
+        jb.A[e] = in ? jb.outA[(long long)perm[i] * jb.n + perm[j]] : 0.0;
+        jb.VT[e] = (i < jb.n ? perm[i] == j : i == j) ? 1.0 : 0.0; /* row i = unit vector of the original coordinate perm[i] */
     }
 }
 /* squared Frobenius norm, one CTA per matrix, fixed summation order (deterministic thresholds) */
@@ -1620,7 +1643,10 @@ __global__ void __launch_bounds__(256) eig_gather_kernel(const EigJob* __restric
 
 int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, double* const* d_w) {
     if (nblocks <= 0) return 0;
-    /* blocks of up to 64 states: one launch of the single-CTA Jacobi kernel */
+    /* blocks of up to 64 states: one launch of the single-CTA Jacobi kernel — on a side stream, beside the block-Jacobi launches
+       of the larger blocks (it took 3.5 ms of every truncation when it ran in front of them) */
+    JacobiJob* d_small = nullptr;
+    bool forked = false;
     {
         std::vector<JacobiJob> jobs;
         for (int b = 0; b < nblocks; ++b) if (n[b] > 0 && n[b] <= JAC_NMAX) jobs.push_back({d_A[b], d_w[b], n[b], 0});
@@ -1628,17 +1654,28 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
             constexpr int smem = 2 * JAC_NMAX * JAC_LD * (int)sizeof(double);
             /* a per-DEVICE attribute: set on every call (cheap), a process may hold contexts on several devices */
             CUDA_OK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            JacobiJob* d_jobs = (JacobiJob*)malloc_bytes(st, jobs.size() * sizeof(JacobiJob));
-            CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(JacobiJob), cudaMemcpyHostToDevice, st->s));
-            jacobi_eig_kernel<<<(int)jobs.size(), JAC_THREADS, smem, st->s>>>(d_jobs);
+            if (!st->aux) {
+                CUDA_OK(cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+                CUDA_OK(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
+            }
+            d_small = (JacobiJob*)malloc_bytes(st, jobs.size() * sizeof(JacobiJob));
+            CUDA_OK(cudaMemcpyAsync(d_small, jobs.data(), jobs.size() * sizeof(JacobiJob), cudaMemcpyHostToDevice, st->s)); /* (pageable source: staged before the call returns) */
+            CUDA_OK(cudaEventRecord(st->ev_fork, st->s));
+            CUDA_OK(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
+            jacobi_eig_kernel<<<(int)jobs.size(), JAC_THREADS, smem, st->aux>>>(d_small);
             LAUNCH_CHECK();
-            CUDA_OK(cudaStreamSynchronize(st->s)); /* the host job list must outlive the copy */
-            free_bytes(st, d_jobs);
+            CUDA_OK(cudaEventRecord(st->ev_join, st->aux));
+            forked = true;
         }
     }
+    /* the main stream continues only when the side stream is done; the job list is freed after that */
+    auto join = [&]() {
+        if (forked) { CUDA_OK(cudaStreamWaitEvent(st->s, st->ev_join, 0)); CUDA_OK(cudaStreamSynchronize(st->s)); free_bytes(st, d_small); forked = false; }
+    };
     std::vector<int> big;
     for (int b = 0; b < nblocks; ++b) if (n[b] > JAC_NMAX) big.push_back(b);
-    if (big.empty()) return 0;
+    if (big.empty()) { join(); return 0; }
     std::stable_sort(big.begin(), big.end(), [&](int a, int b) { return n[a] > n[b]; });
     const int nj = (int)big.size();
     /* one workspace for everything: A, VT (np^2 each), Q (nb/2 x 64 x 64), flags */
@@ -1677,8 +1714,12 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     CUDA_OK(cudaFuncSetAttribute(eig_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, app_smem));
     eig_norm_kernel<<<nj, 1024, 0, st->s>>>(d_jobs);
     LAUNCH_CHECK();
-    eig_init_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs);
+    CUDA_OK(cudaMemcpyAsync(d_tab, rank_off.data(), (size_t)nj * 4, cudaMemcpyHostToDevice, st->s));
+    eig_perm_kernel<<<dim3(4, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab, getenv("DMRGX_JAC_NO_PRESORT") ? 0 : 1); /* (experiment hook) */
     LAUNCH_CHECK();
+    eig_init_kernel<<<dim3(64, nj), 256, 0, st->s>>>(d_jobs, wi, d_tab);
+    LAUNCH_CHECK();
+    CUDA_OK(cudaStreamSynchronize(st->s)); /* d_tab is reused for the prefix tables below */
     /* inner cyclic sweeps per sub-problem: two while the matrix is far from diagonal, one once the sweeps are in their
        convergent phase (tunable for experiments) */
     static const int max_inner = getenv("DMRGX_JAC_INNER") ? atoi(getenv("DMRGX_JAC_INNER")) : 2;
@@ -1775,6 +1816,7 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         LAUNCH_CHECK();
         CUDA_OK(cudaStreamSynchronize(st->s)); /* the host item lists must outlive their copies */
     }
+    join();
     CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables and the workspace die with this scope */
     free_bytes(st, d_items);
     free_bytes(st, d_segs);
