@@ -1350,7 +1350,8 @@ __device__ __forceinline__ int eig_find(const int* __restrict__ prefix, int njob
 }
 
 constexpr int ESUB_THREADS = 1024; /* the sub-problem is latency-bound (three barriers per rotation round): all the threads an SM has */
-__global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner) {
+__global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner,
+                                                               int pattern) {
     extern __shared__ double jsm[];
     double* A = jsm;                 /* [64][65] */
     double* V = jsm + ET * JAC_LD;   /* rotation, columns = eigenvectors */
@@ -1391,11 +1392,19 @@ __global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __r
         if (sweep == 0) off_entry = offsh;
         if (offsh <= thr) break;
         rotated = true;
-        for (int rr = 0; rr < ET - 1; ++rr) {
+        /* inner sweep `sweep` is a FULL cyclic sweep (63 rounds: all 2016 pairs) when bit `sweep` of `pattern` is set, else a
+           CROSS sweep (32 rounds: the 1024 pairs (p in block I, q in block J) only — where the off-diagonal weight sits once
+           both diagonal blocks have been diagonalised by an earlier visit) */
+        const bool full = (pattern >> sweep) & 1;
+        const int nrounds = full ? ET - 1 : EB;
+        for (int rr = 0; rr < nrounds; ++rr) {
             if (tid < ET / 2) {
-                const int a = tid == 0 ? ET - 1 : (rr + tid) % (ET - 1);
-                const int b = (rr + ET - 1 - tid) % (ET - 1);
-                const int p = a < b ? a : b, q = a < b ? b : a;
+                int p, q;
+                if (full) {
+                    const int a = tid == 0 ? ET - 1 : (rr + tid) % (ET - 1);
+                    const int b = (rr + ET - 1 - tid) % (ET - 1);
+                    p = a < b ? a : b; q = a < b ? b : a;
+                } else { p = tid; q = EB + ((tid + rr) & (EB - 1)); }
                 double c = 1.0, sn = 0.0;
                 const double apq = A[p * JAC_LD + q];
                 /* the rotation with |angle| <= pi/4 that zeroes a_pq, with TWO dependent reciprocal square roots and no division
@@ -1725,6 +1734,10 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     static const int max_inner = getenv("DMRGX_JAC_INNER") ? atoi(getenv("DMRGX_JAC_INNER")) : 2;
     static const int late_inner = getenv("DMRGX_JAC_INNER_LATE") ? atoi(getenv("DMRGX_JAC_INNER_LATE")) : 2;
     static const int late_from = getenv("DMRGX_JAC_LATE_FROM") ? atoi(getenv("DMRGX_JAC_LATE_FROM")) : 6;
+    /* bit i: inner sweep i is a full cyclic sweep (else cross pairs only); first sweep of the solve / later sweeps */
+    static const int pattern_first = getenv("DMRGX_JAC_PATTERN_FIRST") ? atoi(getenv("DMRGX_JAC_PATTERN_FIRST")) : 3;
+    static const int pattern_alt = getenv("DMRGX_JAC_PATTERN_ALT") ? atoi(getenv("DMRGX_JAC_PATTERN_ALT")) : 2; /* even sweeps (experiments) */
+    static const int pattern_rest = getenv("DMRGX_JAC_PATTERN") ? atoi(getenv("DMRGX_JAC_PATTERN")) : 2; /* cross, then full: the sweep count of (full, full) at 3/4 of its rounds */
     int sweeps_done = 0;
     /* live jobs are a prefix-compacted copy of the job list (largest first); tables re-uploaded when a matrix finishes */
     std::vector<int> live((size_t)nj);
@@ -1755,7 +1768,8 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         CUDA_OK(cudaStreamSynchronize(st->s)); /* host tables are reused below */
         /* one sweep of the largest live matrix (smaller ones complete at least one sweep of their own in the same rounds) */
         for (int rr = 0; rr < maxnb - 1; ++rr, ++round) {
-            eig_sub_kernel<<<sub_prefix[nl], ESUB_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, sweeps_done >= late_from ? late_inner : max_inner);
+            eig_sub_kernel<<<sub_prefix[nl], ESUB_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, sweeps_done >= late_from ? late_inner : max_inner,
+                                                                                   sweeps_done == 0 ? pattern_first : ((sweeps_done & 1) ? pattern_rest : pattern_alt));
             LAUNCH_CHECK();
             eig_apply_kernel<<<app_prefix[nl], 128, app_smem, st->s>>>(d_live, d_tab + nl + 1, nl, round);
             LAUNCH_CHECK();
