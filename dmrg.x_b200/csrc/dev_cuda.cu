@@ -1351,14 +1351,14 @@ __device__ __forceinline__ int eig_find(const int* __restrict__ prefix, int njob
 
 constexpr int ESUB_THREADS = 1024; /* the sub-problem is latency-bound (three barriers per rotation round): all the threads an SM has */
 __global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __restrict__ jobs, const int* __restrict__ prefix, int njobs, int round, int max_inner,
-                                                               int pattern) {
+                                                               int pattern, double adapt) {
     extern __shared__ double jsm[];
     double* A = jsm;                 /* [64][65] */
     double* V = jsm + ET * JAC_LD;   /* rotation, columns = eigenvectors */
     __shared__ double cs[ET / 2][2];
     __shared__ int pq[ET / 2][2];
-    __shared__ double red[ESUB_THREADS / 32];
-    __shared__ double offsh;
+    __shared__ double red[ESUB_THREADS / 32], redw[ESUB_THREADS / 32];
+    __shared__ double offsh, offwsh;
     int k;
     const EigJob jb = jobs[eig_find(prefix, njobs, blockIdx.x, k)];
     const int tid = threadIdx.x, np = jb.np;
@@ -1378,16 +1378,16 @@ __global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __r
     bool rotated = false;
     double off_entry = 0.0;
     for (int sweep = 0; sweep < max_inner; ++sweep) {
-        double off = 0.0;
+        double off = 0.0, offw = 0.0; /* off-diagonal weight: all of it / the part inside the two diagonal blocks */
         for (int e = tid; e < ET * ET; e += ESUB_THREADS) {
             const int i = e >> 6, j = e & 63;
             const double a = A[i * JAC_LD + j];
-            if (i != j) off += a * a;
+            if (i != j) { off += a * a; if ((i < EB) == (j < EB)) offw += a * a; }
         }
-        off = warp_sum(off);
-        if ((tid & 31) == 0) red[tid >> 5] = off;
+        off = warp_sum(off); offw = warp_sum(offw);
+        if ((tid & 31) == 0) { red[tid >> 5] = off; redw[tid >> 5] = offw; }
         __syncthreads();
-        if (tid == 0) { double o = 0; for (int w = 0; w < ESUB_THREADS / 32; ++w) o += red[w]; offsh = o; }
+        if (tid == 0) { double o = 0, ow = 0; for (int w = 0; w < ESUB_THREADS / 32; ++w) { o += red[w]; ow += redw[w]; } offsh = o; offwsh = ow; }
         __syncthreads();
         if (sweep == 0) off_entry = offsh;
         if (offsh <= thr) break;
@@ -1395,7 +1395,7 @@ __global__ void __launch_bounds__(ESUB_THREADS) eig_sub_kernel(const EigJob* __r
         /* inner sweep `sweep` is a FULL cyclic sweep (63 rounds: all 2016 pairs) when bit `sweep` of `pattern` is set, else a
            CROSS sweep (32 rounds: the 1024 pairs (p in block I, q in block J) only — where the off-diagonal weight sits once
            both diagonal blocks have been diagonalised by an earlier visit) */
-        const bool full = (pattern >> sweep) & 1;
+        const bool full = ((pattern >> sweep) & 1) && offwsh > adapt * offsh;
         const int nrounds = full ? ET - 1 : EB;
         for (int rr = 0; rr < nrounds; ++rr) {
             if (tid < ET / 2) {
@@ -1736,6 +1736,9 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
     static const int late_from = getenv("DMRGX_JAC_LATE_FROM") ? atoi(getenv("DMRGX_JAC_LATE_FROM")) : 6;
     /* bit i: inner sweep i is a full cyclic sweep (else cross pairs only); first sweep of the solve / later sweeps */
     static const int pattern_first = getenv("DMRGX_JAC_PATTERN_FIRST") ? atoi(getenv("DMRGX_JAC_PATTERN_FIRST")) : 3;
+    /* a full sweep is replaced by a cross sweep while the weight inside the diagonal blocks is below this fraction of the sub-problem's
+       off-diagonal weight (0: never) */
+    static const double adapt = getenv("DMRGX_JAC_ADAPT") ? atof(getenv("DMRGX_JAC_ADAPT")) : 0.0;
     static const int pattern_alt = getenv("DMRGX_JAC_PATTERN_ALT") ? atoi(getenv("DMRGX_JAC_PATTERN_ALT")) : 2; /* even sweeps (experiments) */
     static const int pattern_rest = getenv("DMRGX_JAC_PATTERN") ? atoi(getenv("DMRGX_JAC_PATTERN")) : 2; /* cross, then full: the sweep count of (full, full) at 3/4 of its rounds */
     int sweeps_done = 0;
@@ -1769,7 +1772,7 @@ int syevd_batch(Stream* st, int nblocks, const int* n, double* const* d_A, doubl
         /* one sweep of the largest live matrix (smaller ones complete at least one sweep of their own in the same rounds) */
         for (int rr = 0; rr < maxnb - 1; ++rr, ++round) {
             eig_sub_kernel<<<sub_prefix[nl], ESUB_THREADS, sub_smem, st->s>>>(d_live, d_tab, nl, round, sweeps_done >= late_from ? late_inner : max_inner,
-                                                                                   sweeps_done == 0 ? pattern_first : ((sweeps_done & 1) ? pattern_rest : pattern_alt));
+                                                                                   sweeps_done == 0 ? pattern_first : ((sweeps_done & 1) ? pattern_rest : pattern_alt), adapt);
             LAUNCH_CHECK();
             eig_apply_kernel<<<app_prefix[nl], 128, app_smem, st->s>>>(d_live, d_tab + nl + 1, nl, round);
             LAUNCH_CHECK();
