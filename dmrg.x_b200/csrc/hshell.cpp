@@ -623,6 +623,18 @@ static void plan_halo(HShell* H, const Kron* kron, const std::vector<Group>& gro
 
 static HShell* build_sharded(const Kron* kron, const std::vector<Group>& groups, int nterms) {
     Ctx* ctx = kron->ctx;
+    if (ctx->world <= 1 && getenv("DMRGX_FAKE_WORLD")) {
+        /* profiling hook: plan and run ONE rank's shard of a `world`-way split on a single GPU (ncu is single-GPU only); the rows
+           outside the shard are not computed */
+        const int fw = std::max(1, atoi(getenv("DMRGX_FAKE_WORLD"))), fr = std::min(fw - 1, std::max(0, getenv("DMRGX_FAKE_RANK") ? atoi(getenv("DMRGX_FAKE_RANK")) : 0));
+        long long gb = 0; double gf = 0;
+        const std::vector<long long> cuts = shard_rows(kron, groups, nterms, fw, gb, gf);
+        HShell* H = build_shell(kron, groups, nterms, cuts[(size_t)fr], cuts[(size_t)fr + 1]);
+        H->row_begin = 0; H->row_end = H->n; /* host-buffer entry points keep working on the whole vector */
+        H->row_cuts = {0, H->n};
+        H->alg_bytes_global = gb; H->alg_flops_global = gf;
+        return H;
+    }
     if (ctx->world <= 1) {
         HShell* H = build_shell(kron, groups, nterms);
         H->row_cuts = {0, H->n};
