@@ -68,6 +68,7 @@ struct Stream {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     int spmm_smem = 0;           /* dynamic shared memory spmm_kernel has been configured for on this device */
+    bool chain_cfg = false;      /* chain_kernel's dynamic shared memory attribute has been set on this device */
     cudaStream_t aux = nullptr;  /* side stream: the small-block eigensolver runs beside the block-Jacobi launches */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -210,6 +211,10 @@ constexpr int BM = 64, BK = 16, NTHREADS = 128;
 constexpr int S_MK = BK + 4;  /* [m][k] layout row stride (20 ≡ 4 mod 16) */
 constexpr int S_KM = BM + 4;  /* [k][m] layout row stride (68 ≡ 4 mod 16) */
 constexpr int SMEM_TILE = (BM * S_MK > BK * S_KM) ? BM * S_MK : BK * S_KM; /* 1280 doubles */
+/* NSTAGE (template parameter of the kernel): depth of the cp.async ring — chunks c+1 .. c+NSTAGE-1 are in flight while chunk c is
+   multiplied.  Two stages are best when the launch is large and its operands are L2-warm (m = 2048: 1.264 vs 1.294 ms); three win
+   when the work items are few and every operand is a cold DRAM miss (one rank's shard of an 8-GPU apply: stage 2 0.158 -> 0.121 ms):
+   run_chain picks by the size of the launch (profiles/r2_chain_kernel.md). */
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -295,7 +300,7 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[4][4][2], const double* 
     }
 }
 
-template <bool A_MK, bool B_NK, bool FULL, bool UNIT>
+template <int NSTAGE, bool A_MK, bool B_NK, bool FULL, bool UNIT>
 __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                              int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
     Stager<A_MK> sa;
@@ -309,21 +314,26 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
     constexpr int b_sn = B_NK ? S_MK : 1, b_sk = B_NK ? 1 : S_KM;
     const int a_base = (rbase + g) * a_sm + t * a_sk;
     const int b_base = (cbase + g) * b_sn + t * b_sk;
-    __syncthreads(); /* the previous segment's readers are done with both stages */
-    sa.issue(As, K);
-    sb.issue(Bs, K);
-    cp_async_commit();
-    for (int c = 0; c < nchunks; ++c) {
-        const int cur = c & 1;
-        if (c + 1 < nchunks) {
-            const int krem = K - (c + 1) * BK;
-            sa.issue(As + (cur ^ 1) * SMEM_TILE, krem);
-            sb.issue(Bs + (cur ^ 1) * SMEM_TILE, krem);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    __syncthreads(); /* the previous segment's readers are done with every stage */
+    /* prologue: the first NSTAGE-1 chunks; a group is committed for every slot (empty past the end) so that the wait below
+       always means "all but the NSTAGE-1 most recent groups", i.e. chunk c, have landed */
+#pragma unroll
+    for (int p = 0; p < NSTAGE - 1; ++p) {
+        if (p < nchunks) {
+            sa.issue(As + p * SMEM_TILE, K - p * BK);
+            sb.issue(Bs + p * SMEM_TILE, K - p * BK);
         }
+        cp_async_commit();
+    }
+    int cur = 0, nxt = NSTAGE - 1;
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + NSTAGE - 1 < nchunks) {
+            const int krem = K - (c + NSTAGE - 1) * BK;
+            sa.issue(As + nxt * SMEM_TILE, krem);
+            sb.issue(Bs + nxt * SMEM_TILE, krem);
+        }
+        cp_async_commit();
+        cp_async_wait<NSTAGE - 1>();
         __syncthreads();
         const double* as = As + cur * SMEM_TILE + a_base;
         const double* bs = Bs + cur * SMEM_TILE + b_base;
@@ -343,24 +353,28 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
 #undef MMA_CASE
         }
         __syncthreads();
+        cur = cur + 1 == NSTAGE ? 0 : cur + 1;
+        nxt = nxt + 1 == NSTAGE ? 0 : nxt + 1;
     }
 }
 
-template <bool A_MK, bool B_NK>
+template <int NSTAGE, bool A_MK, bool B_NK>
 __device__ __forceinline__ void gemm_dispatch(double (&acc)[4][4][2], const Segment& sg, const WorkItem& it, double* As, double* Bs,
                                               int tid, int rbase, int cbase, int g, int t, int nmi, int nni) {
     /* block-uniform choice: every warp of a 64×64 tile has 4×4 fragments */
     if (sg.coef == 1.0) {
-        if (it.tm == BM && it.tn == BM) gemm_segment<A_MK, B_NK, true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, 4, 4);
-        else gemm_segment<A_MK, B_NK, false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
-    } else gemm_segment<A_MK, B_NK, false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+        if (it.tm == BM && it.tn == BM) gemm_segment<NSTAGE, A_MK, B_NK, true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, 4, 4);
+        else gemm_segment<NSTAGE, A_MK, B_NK, false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+    } else gemm_segment<NSTAGE, A_MK, B_NK, false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
 }
 
+template <int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __restrict__ items, const Segment* __restrict__ segs,
                                                             const double* __restrict__ xbase, double* __restrict__ ybase,
                                                             double* __restrict__ wbase) {
-    __shared__ double As[2 * SMEM_TILE];
-    __shared__ double Bs[2 * SMEM_TILE];
+    extern __shared__ __align__(16) double chain_smem[];
+    double* As = chain_smem;
+    double* Bs = chain_smem + NSTAGE * SMEM_TILE;
     WorkItem it = items[blockIdx.x];
     if (it.c_in_y) it.C = (double*)((char*)(it.c_in_y == 1 ? ybase : wbase) + (size_t)it.C);
     const int tid = threadIdx.x;
@@ -389,11 +403,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
             const bool a_mk = (sg.lda_k == 1) || (sg.lda_m != 1);
             const bool b_nk = (sg.ldb_k == 1) || (sg.ldb_n != 1);
             if (a_mk) {
-                if (b_nk) gemm_dispatch<true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
-                else gemm_dispatch<true, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                if (b_nk) gemm_dispatch<NSTAGE, true, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                else gemm_dispatch<NSTAGE, true, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
             } else {
-                if (b_nk) gemm_dispatch<false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
-                else gemm_dispatch<false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                if (b_nk) gemm_dispatch<NSTAGE, false, true>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
+                else gemm_dispatch<NSTAGE, false, false>(acc, sg, it, As, Bs, tid, rbase, cbase, g, t, nmi, nni);
             }
         } else if (sg.type == SEG_AXPY) {
             /* acc += coef * A(m,n): all of a thread's (up to 32) loads are issued before the first use */
@@ -516,7 +530,15 @@ __global__ void __launch_bounds__(NTHREADS, 3) chain_kernel(const WorkItem* __re
 
 void run_chain(Stream* st, const WorkItem* d_items, int nitems, const Segment* d_segs, const double* x, double* y, double* w) {
     if (nitems <= 0) return;
-    chain_kernel<<<nitems, NTHREADS, 0, st->s>>>(d_items, d_segs, x, y, w);
+    constexpr int smem2 = 2 * 2 * SMEM_TILE * (int)sizeof(double), smem3 = 2 * 3 * SMEM_TILE * (int)sizeof(double);
+    if (!st->chain_cfg) { /* a per-device attribute, set once per context */
+        CUDA_OK(cudaFuncSetAttribute(chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        st->chain_cfg = true;
+    }
+    /* fewer than four waves of the 444 resident CTAs: the deeper copy ring (cold operands, short items) */
+    static const int deep_below = getenv("DMRGX_CHAIN_DEEP_BELOW") ? atoi(getenv("DMRGX_CHAIN_DEEP_BELOW")) : 1800;
+    if (nitems < deep_below) chain_kernel<3><<<nitems, NTHREADS, smem3, st->s>>>(d_items, d_segs, x, y, w);
+    else chain_kernel<2><<<nitems, NTHREADS, smem2, st->s>>>(d_items, d_segs, x, y, w);
     LAUNCH_CHECK();
 }
 
