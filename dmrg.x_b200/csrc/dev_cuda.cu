@@ -244,14 +244,19 @@ struct Stager {
     long long kstep;     /* pointer advance per chunk, in elements */
     int soff;            /* smem offset of element 0; element i is at soff + i*SI */
     int k0;              /* k index of element 0 inside a chunk (element i: k0 for MK, k0 + 2i otherwise) */
+    unsigned rowmask;    /* bit i: element i lies in a row of the tile (rows beyond a ragged tile's extent are not staged at all:
+                            their shared-memory lines keep stale data that only reaches accumulator rows / columns never stored) */
     static constexpr int SI = MK ? 8 * S_MK : 2 * S_KM;
     __device__ __forceinline__ void init(const double* b, long long ld_row, long long ld_k, int ext, int tid) {
         base = b;
         if (MK) {
             const int k = tid & 15, r0 = tid >> 4;
+            rowmask = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int r = r0 + 8 * i; r = r < ext ? r : ext - 1;
+                int r = r0 + 8 * i;
+                if (r < ext) rowmask |= 1u << i;
+                r = r < ext ? r : ext - 1;
                 off[i] = (int)(r * ld_row + k * ld_k);
             }
             soff = r0 * S_MK + k;
@@ -259,6 +264,7 @@ struct Stager {
         } else {
             const int r = tid & 63, kk = tid >> 6;
             const int rc = r < ext ? r : ext - 1;
+            rowmask = r < ext ? 0xffu : 0u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) off[i] = (int)(rc * ld_row + (kk + 2 * i) * ld_k);
             soff = kk * S_KM + r;
@@ -266,12 +272,13 @@ struct Stager {
         }
         kstep = (long long)BK * ld_k;
     }
-    /* krem = K - k0 of this chunk (>= 1) */
+    /* krem = K - k0 of this chunk (>= 1); ALLROWS: a full tile, no row is skipped */
+    template <bool ALLROWS>
     __device__ __forceinline__ void issue(double* sm, int krem) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool v = (MK ? k0 : k0 + 2 * i) < krem;
-            cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
+            if (ALLROWS || ((rowmask >> i) & 1u)) cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
         }
         base += kstep;
     }
@@ -320,8 +327,8 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
 #pragma unroll
     for (int p = 0; p < NSTAGE - 1; ++p) {
         if (p < nchunks) {
-            sa.issue(As + p * SMEM_TILE, K - p * BK);
-            sb.issue(Bs + p * SMEM_TILE, K - p * BK);
+            sa.template issue<FULL>(As + p * SMEM_TILE, K - p * BK);
+            sb.template issue<FULL>(Bs + p * SMEM_TILE, K - p * BK);
         }
         cp_async_commit();
     }
@@ -329,8 +336,8 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
     for (int c = 0; c < nchunks; ++c) {
         if (c + NSTAGE - 1 < nchunks) {
             const int krem = K - (c + NSTAGE - 1) * BK;
-            sa.issue(As + nxt * SMEM_TILE, krem);
-            sb.issue(Bs + nxt * SMEM_TILE, krem);
+            sa.template issue<FULL>(As + nxt * SMEM_TILE, krem);
+            sb.template issue<FULL>(Bs + nxt * SMEM_TILE, krem);
         }
         cp_async_commit();
         cp_async_wait<NSTAGE - 1>();
