@@ -159,7 +159,10 @@ constexpr int MAX_BASIS = 39; /* largest ncv the fused kernels take (eigs_smalle
 void gs_pass(Stream*, const double* V, long long ldv, int nvec, double* w, long long n, const double* d_coef, double* d_dots, double* d_nrm2);
 /* Last step of the two-pass Gram-Schmidt, fused with the normalisation (no reduction, no all-reduce):
        vout = (w - Σ_i d_coef[i]·V_i) / sqrt(b2),   b2 = *d_nrm2_in - Σ_i d_coef[i]²   (Pythagoras: d_nrm2_in is ||w||² BEFORE the update
-   and the coefficients of a second pass are round-off sized, so there is no cancellation);  *d_nrm2_out = b2.  nvec <= MAX_BASIS + 1. */
+   and the coefficients of a second pass are round-off sized, so there is no cancellation);  *d_nrm2_out = b2.  nvec <= MAX_BASIS + 1.
+   Refinement "if needed" (what SLEPc's default orthogonalisation does with a much looser test): when Σ_i d_coef[i]² <=
+   GS_REFINE_REL² · *d_nrm2_in the correction is not applied — vout = w / sqrt(*d_nrm2_in), b2 = *d_nrm2_in — and V is not read. */
+constexpr double GS_REFINE_REL = 1e-12;
 void gs_final(Stream*, const double* V, long long ldv, int nvec, const double* w, long long n, const double* d_coef, const double* d_nrm2_in,
               double* d_nrm2_out, double* vout);
 /* v = w / sqrt(*d_nrm2) */

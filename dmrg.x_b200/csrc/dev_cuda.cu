@@ -62,8 +62,8 @@ struct Stream {
     struct Arena { char* base = nullptr; size_t size = 0; std::map<size_t, size_t> free; /* offset -> length of the free ranges */ };
     std::vector<Arena> arenas;   /* what was actually cudaMalloc'ed */
     std::unordered_map<void*, size_t> live;
-    size_t bytes_reserved = 0;
-    double malloc_seconds = 0;   /* time spent in cudaMalloc by the caching allocator (DMRGX_TRACE prints it at the end) */
+    size_t bytes_reserved = 0, bytes_free = 0, bytes_live = 0, bytes_live_peak = 0;
+    double malloc_seconds = 0;   /* time spent in cudaMalloc for the heap (DMRGX_TRACE / DMRGX_ALLOC_STATS print it at the end) */
     long long malloc_calls = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -106,8 +106,9 @@ void destroy(Stream* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     cudaStreamSynchronize(st->s);
-    if (getenv("DMRGX_TRACE"))
-        fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved\n", st->malloc_calls, st->malloc_seconds, st->bytes_reserved / 1e9);
+    if (getenv("DMRGX_TRACE") || getenv("DMRGX_ALLOC_STATS"))
+        fprintf(stderr, "[trace] allocator: %lld cudaMalloc calls, %.3f s, %.2f GB reserved, peak in use %.2f GB\n", st->malloc_calls, st->malloc_seconds,
+                st->bytes_reserved / 1e9, st->bytes_live_peak / 1e9);
     if (st->comm) comm_destroy_(st);
     if (st->aux) cudaStreamDestroy(st->aux);
     if (st->ev_fork) cudaEventDestroy(st->ev_fork);
@@ -126,12 +127,17 @@ void* raw_stream(Stream* st) { return (void*)st->s; }
 /* Device memory: a stream-ordered heap.  A DMRG sweep frees and allocates panels of slowly varying sizes every step; handing
    each one back to the driver (cudaFreeAsync) let the pool fragment and re-map (200-700 ms stalls inside single steps), and
    round 1's size-class free lists reserved 65 GB for a 12x6 m = 2048 run once the eigensolver workspaces joined the mix
-   (profiles/r2_eigensolver.md).  Now: arenas of >= 1 GiB from cudaMalloc, inside them a classic best-fit heap with splitting
+   (profiles/r2_eigensolver.md).  Now: arenas of 1-8 GiB from cudaMalloc, inside them a classic best-fit heap with splitting
    and coalescing of free ranges.  Everything is ordered on the one stream of the context, so a freed range can be handed out
    again immediately: its new user is queued behind its old one. */
+constexpr size_t HEAP_SLAB = (size_t)1 << 30, HEAP_GRAIN = (size_t)256 << 20;
+static void heap_add_arena(Stream* st, void* slab, size_t sz) {
+    Stream::Arena ar; ar.base = (char*)slab; ar.size = sz; ar.free[0] = sz;
+    st->arenas.push_back(ar); st->bytes_reserved += sz; st->bytes_free += sz;
+}
 void* malloc_bytes(Stream* st, size_t bytes) {
     const size_t need = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (;;) {
         /* best fit over the free ranges of all arenas */
         Stream::Arena* best_a = nullptr;
         std::map<size_t, size_t>::iterator best;
@@ -145,12 +151,15 @@ void* malloc_bytes(Stream* st, size_t bytes) {
             if (len > need) best_a->free[off + need] = len - need;
             void* p = best_a->base + off;
             st->live[p] = need;
+            st->bytes_free -= need; st->bytes_live += need;
+            if (st->bytes_live > st->bytes_live_peak) st->bytes_live_peak = st->bytes_live;
             return p;
         }
-        if (attempt == 1) break;
-        /* a new arena: 1 GiB, or the request rounded up to 256 MiB when larger */
-        constexpr size_t SLAB = (size_t)1 << 30, GRAIN = (size_t)256 << 20;
-        const size_t sz = std::max(SLAB, (need + GRAIN - 1) / GRAIN * GRAIN);
+        /* a new arena: 1 GiB, a quarter of what is already reserved (at most 8 GiB: the 0.4-1.5 GB blocks and workspaces of a
+           large sweep pack poorly into 1 GiB arenas — 53 GB reserved for 37 GB in use on the 12x6 m = 2048 run), or the
+           request rounded up to 256 MiB when larger */
+        const size_t quarter = std::min(HEAP_SLAB * 8, st->bytes_reserved / 4 / HEAP_GRAIN * HEAP_GRAIN);
+        const size_t sz = std::max(std::max(HEAP_SLAB, quarter), (need + HEAP_GRAIN - 1) / HEAP_GRAIN * HEAP_GRAIN);
         void* slab = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMalloc(&slab, sz);
@@ -160,20 +169,17 @@ void* malloc_bytes(Stream* st, size_t bytes) {
             CUDA_OK(cudaStreamSynchronize(st->s));
             for (size_t i = 0; i < st->arenas.size();) {
                 Stream::Arena& ar = st->arenas[i];
-                if (ar.free.size() == 1 && ar.free.begin()->second == ar.size) { cudaFree(ar.base); st->bytes_reserved -= ar.size; st->arenas.erase(st->arenas.begin() + (long)i); }
-                else ++i;
+                if (ar.free.size() == 1 && ar.free.begin()->second == ar.size) {
+                    cudaFree(ar.base); st->bytes_reserved -= ar.size; st->bytes_free -= ar.size; st->arenas.erase(st->arenas.begin() + (long)i);
+                } else ++i;
             }
             e = cudaMalloc(&slab, need);
-            if (e == cudaSuccess) { Stream::Arena ar; ar.base = (char*)slab; ar.size = need; ar.free[0] = need; st->arenas.push_back(ar); st->bytes_reserved += need; }
-        } else {
-            Stream::Arena ar; ar.base = (char*)slab; ar.size = sz; ar.free[0] = sz;
-            st->arenas.push_back(ar); st->bytes_reserved += sz;
-        }
+            if (e == cudaSuccess) heap_add_arena(st, slab, need);
+        } else heap_add_arena(st, slab, sz);
         st->malloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         st->malloc_calls++;
-        CUDA_OK(e);
+        CUDA_OK(e); /* throws when the device is full; otherwise the new arena holds the request and the next pass returns */
     }
-    throw std::runtime_error("device allocator: no room after growing the heap");
 }
 void free_bytes(Stream* st, void* p) {
     if (!p) return;
@@ -181,6 +187,7 @@ void free_bytes(Stream* st, void* p) {
     if (f == st->live.end()) return;
     size_t len = f->second;
     st->live.erase(f);
+    st->bytes_free += len; st->bytes_live -= len;
     for (auto& ar : st->arenas) {
         if ((char*)p < ar.base || (char*)p >= ar.base + ar.size) continue;
         size_t off = (size_t)((char*)p - ar.base);
@@ -220,6 +227,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     int sz = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8_all(double* smem_dst, const double* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -275,10 +286,16 @@ struct Stager {
     /* krem = K - k0 of this chunk (>= 1); ALLROWS: a full tile, no row is skipped */
     template <bool ALLROWS>
     __device__ __forceinline__ void issue(double* sm, int krem) {
+        if (krem >= BK) { /* block-uniform: every chunk but a segment's last one — no K predicate, no pointer select */
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool v = (MK ? k0 : k0 + 2 * i) < krem;
-            if (ALLROWS || ((rowmask >> i) & 1u)) cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
+            for (int i = 0; i < 8; ++i)
+                if (ALLROWS || ((rowmask >> i) & 1u)) cp_async8_all(sm + soff + i * SI, base + off[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool v = (MK ? k0 : k0 + 2 * i) < krem;
+                if (ALLROWS || ((rowmask >> i) & 1u)) cp_async8(sm + soff + i * SI, v ? base + off[i] : base, v);
+            }
         }
         base += kstep;
     }
@@ -289,12 +306,12 @@ struct Stager {
    are).  Otherwise the generic variant: fragment counts and the coefficient are runtime values.  Two variants per
    operand layout keep the kernel small enough for the instruction caches. */
 /* the DMMAs of one 16-deep chunk for a warp that owns NMI x NNI fragments */
-template <bool A_MK, bool B_NK, bool UNIT, int NMI, int NNI>
+template <bool A_MK, bool B_NK, bool UNIT, int NMI, int NNI, int NKK = BK / 4>
 __device__ __forceinline__ void chunk_mma(double (&acc)[4][4][2], const double* as, const double* bs, double coef) {
     constexpr int a_sm = A_MK ? S_MK : 1, a_sk = A_MK ? 1 : S_KM;
     constexpr int b_sn = B_NK ? S_MK : 1, b_sk = B_NK ? 1 : S_KM;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
+    for (int kk = 0; kk < NKK; ++kk) {
         double a[NMI], b[NNI];
 #pragma unroll
         for (int mi = 0; mi < NMI; ++mi) a[mi] = as[mi * 8 * a_sm + kk * 4 * a_sk];
@@ -332,6 +349,7 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
         }
         cp_async_commit();
     }
+    /* (a one-barrier-per-chunk ring — wait, barrier, then refill the stage of chunk c-1 — was measured: 0.2 % slower) */
     int cur = 0, nxt = NSTAGE - 1;
     for (int c = 0; c < nchunks; ++c) {
         if (c + NSTAGE - 1 < nchunks) {
@@ -345,7 +363,12 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[4][4][2], const Segme
         const double* as = As + cur * SMEM_TILE + a_base;
         const double* bs = Bs + cur * SMEM_TILE + b_base;
         if (FULL) {
-            chunk_mma<A_MK, B_NK, UNIT, 4, 4>(acc, as, bs, coef);
+            /* the last chunk of a segment holds K mod 16 columns: only the 4-deep steps that contain any are run */
+            const int krem = K - c * BK;
+            if (krem > 12) chunk_mma<A_MK, B_NK, UNIT, 4, 4, 4>(acc, as, bs, coef);
+            else if (krem > 8) chunk_mma<A_MK, B_NK, UNIT, 4, 4, 3>(acc, as, bs, coef);
+            else if (krem > 4) chunk_mma<A_MK, B_NK, UNIT, 4, 4, 2>(acc, as, bs, coef);
+            else chunk_mma<A_MK, B_NK, UNIT, 4, 4, 1>(acc, as, bs, coef);
         } else {
             /* ragged tile: the fragment counts of this warp select a body compiled for exactly that many DMMAs — a predicated-off
                DMMA still occupies the tensor pipe (a 32x32 tile took as long as a 64x64 one) */
@@ -964,23 +987,35 @@ __global__ void __launch_bounds__(256) gs_final_kernel(const double* __restrict_
                                                        double* __restrict__ vout) {
     __shared__ double c[NV];
     __shared__ double inv;
+    __shared__ bool skip;
     if (threadIdx.x < NV) c[threadIdx.x] = threadIdx.x < nvec ? coef[threadIdx.x] : 0.0;
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int i = 0; i < nvec; ++i) s += c[i] * c[i]; /* fixed order: every block (and every rank) gets the same bits */
-        double b2 = *nrm2_in - s;
+        const double nin = *nrm2_in;
+        /* refinement "if needed": a second-pass correction below GS_REFINE_REL of the vector's norm is not applied (the basis
+           stays orthogonal to 1e-12, far inside what the Ritz values need); the pass is then one read and one write of w */
+        const bool sk = s <= GS_REFINE_REL * GS_REFINE_REL * nin;
+        double b2 = sk ? nin : nin - s;
         if (!(b2 > 0.0)) b2 = 0.0;
         inv = b2 > 0.0 ? 1.0 / sqrt(b2) : 0.0;
+        skip = sk;
         if (blockIdx.x == 0) *nrm2_out = b2;
     }
     __syncthreads();
     const double sc = inv;
+    if (skip) {
+        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) vout[q] = w[q] * sc;
+        return;
+    }
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        double v[NV]; /* every load is issued before the first use */
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = i < nvec ? V[i * ldv + q] : 0.0;
         double acc = w[q];
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-            if (i < nvec) acc -= c[i] * V[i * ldv + q];
+        for (int i = 0; i < NV; ++i) acc -= c[i] * v[i];
         vout[q] = acc * sc;
     }
 }

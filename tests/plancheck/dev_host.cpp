@@ -154,11 +154,12 @@ void gs_final(Stream*, const double* V, long long ldv, int nvec, const double* w
     ++g_launches;
     double s = 0;
     for (int i = 0; i < nvec; ++i) s += coef[i] * coef[i];
-    double b2 = *nrm2_in - s;
+    const bool skip = s <= GS_REFINE_REL * GS_REFINE_REL * *nrm2_in;
+    double b2 = skip ? *nrm2_in : *nrm2_in - s;
     if (!(b2 > 0.0)) b2 = 0.0;
     const double inv = b2 > 0.0 ? 1.0 / std::sqrt(b2) : 0.0;
     *nrm2_out = b2;
-    for (long long q = 0; q < n; ++q) { double a = w[q]; for (int i = 0; i < nvec; ++i) a -= coef[i] * V[i * ldv + q]; vout[q] = a * inv; }
+    for (long long q = 0; q < n; ++q) { double a = w[q]; if (!skip) for (int i = 0; i < nvec; ++i) a -= coef[i] * V[i * ldv + q]; vout[q] = a * inv; }
 }
 void scale_inv_norm(Stream*, const double* w, const double* nrm2, double* v, long long n) {
     ++g_launches;
