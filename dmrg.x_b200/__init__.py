@@ -391,14 +391,18 @@ class HShell:
         _chk(lib().dmrgx_hshell_apply_host(self.h, _p(x), _p(y)))
         return y
 
-    def EPSSolve(self, tol=1e-8, ncv=16, max_it=0, seed=20261018, psi=None):
-        """EPSSolve + EPSGetEigenpair(0) — include/DMRGBlockContainer.hpp:1484-1500"""
+    def EPSSolve(self, tol=1e-8, ncv=16, max_it=0, seed=20261018, psi=None, initial=None):
+        """EPSSolve + EPSGetEigenpair(0) — include/DMRGBlockContainer.hpp:1484-1500.  `initial` (a DeviceVector of the global
+        length) is the extension dmrgx_eigs_smallest_from: the reference always starts from a random vector."""
         if psi is None:
             psi = DeviceVector(self.ctx, self.n)
         o = EigsOpts(tol, ncv, max_it, seed)
         s = EigsStats()
         e0 = C.c_double()
-        _chk(lib().dmrgx_eigs_smallest(self.h, C.byref(o), C.byref(e0), psi.ptr, C.byref(s)))
+        if initial is None:
+            _chk(lib().dmrgx_eigs_smallest(self.h, C.byref(o), C.byref(e0), psi.ptr, C.byref(s)))
+        else:
+            _chk(lib().dmrgx_eigs_smallest_from(self.h, C.byref(o), initial.ptr, C.byref(e0), psi.ptr, C.byref(s)))
         return e0.value, psi, dict(nmatvec=s.nmatvec, nrestart=s.nrestart, converged=bool(s.converged), resid=s.resid)
 
     def expect(self, psi):
@@ -443,6 +447,28 @@ def GetTruncation(kron, psi, mstates):
     l, r = C.c_void_p(), C.c_void_p()
     _chk(lib().dmrgx_truncate(kron.h, psi.ptr, LL(mstates), C.byref(l), C.byref(r)))
     return BasisTransformation(kron.ctx, l), BasisTransformation(kron.ctx, r)
+
+
+class Wave:
+    """EXTENSION (csrc/predict.cpp): this step's ground state with the growing side projected on its kept states;
+    `apply` returns the start vector of the next step's eigen-solve, or None when the blocks do not chain up."""
+
+    def __init__(self, kron, psi, bt_grown, grow_left=True):
+        self.ctx = kron.ctx
+        h = C.c_void_p()
+        _chk(lib().dmrgx_wave_create(kron.h, psi.ptr, bt_grown.h, 1 if grow_left else 0, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().dmrgx_wave_destroy(self.h)
+            self.h = None
+
+    def apply(self, bt_shrinking, site, kron_new):
+        out = DeviceVector(self.ctx, kron_new.NumStates())
+        ok = C.c_int(0)
+        _chk(lib().dmrgx_wave_apply(self.h, bt_shrinking.h, site.h, kron_new.h, out.ptr, C.byref(ok)))
+        return out if ok.value else None
 
 
 def RotateOperators(enlarged, bt):

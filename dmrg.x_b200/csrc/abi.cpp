@@ -260,6 +260,28 @@ int dmrgx_eigs_smallest(dmrgx_hshell h, const dmrgx_eigs_opts* opts, double* e0,
     });
 }
 
+int dmrgx_eigs_smallest_from(dmrgx_hshell h, const dmrgx_eigs_opts* opts, const double* d_initial, double* e0, double* d_psi, dmrgx_eigs_stats* stats) {
+    return guard([&] {
+        EigsOpts o;
+        if (opts) { o.tol = opts->tol; o.ncv = (int)opts->ncv; o.max_it = (int)opts->max_it; o.seed = opts->seed; }
+        if (o.tol <= 0) o.tol = 1e-8;
+        if (o.ncv <= 0) o.ncv = 16;
+        EigsStats s;
+        *e0 = eigs_smallest(H(h), o, d_psi, &s, d_initial);
+        if (stats) { stats->nmatvec = s.nmatvec; stats->nrestart = s.nrestart; stats->converged = s.converged; stats->resid = s.resid; }
+    });
+}
+
+int dmrgx_wave_create(dmrgx_kron k, const double* d_psi, dmrgx_xform grown_side, int grow_left, dmrgx_wave* out) {
+    *out = nullptr;
+    return guard([&] { *out = (dmrgx_wave)wave_create(K(k), d_psi, X(grown_side), grow_left != 0); });
+}
+int dmrgx_wave_apply(dmrgx_wave w, dmrgx_xform shrinking_side, dmrgx_block site, dmrgx_kron k_new, double* d_psi_new, int* ok) {
+    *ok = 0;
+    return guard([&] { *ok = wave_apply((const Wave*)w, X(shrinking_side), B(site), K(k_new), d_psi_new) ? 1 : 0; });
+}
+int dmrgx_wave_destroy(dmrgx_wave w) { return guard([&] { delete (Wave*)w; }); }
+
 int dmrgx_truncate(dmrgx_kron k, const double* d_psi, dmrgx_int mstates, dmrgx_xform* left, dmrgx_xform* right) {
     *left = nullptr; *right = nullptr;
     return guard([&] {

@@ -197,6 +197,18 @@ struct XForm {
     int nstates_old = 0;
 };
 
+/* This step's ground state with the growing side already projected onto its kept states (predict.cpp) */
+struct Wave {
+    Ctx* ctx = nullptr;
+    bool grow_left = true;
+    Sectors grown;                   /* sectors of the new block on the growing side */
+    std::vector<double> other_qn;    /* sectors of the old ENLARGED block on the other side */
+    std::vector<int> other_size;
+    struct Blk { int kg, io; long long off, src; }; /* kept sector of the grown side, enlarged sector of the other side */
+    std::vector<Blk> blks;
+    BufRef phi;
+};
+
 /* DMRGX_TRACE=1: wall-clock of the sub-phases of the host-side orchestration (device drained at each mark), to stderr */
 struct Trace {
     Ctx* ctx; const char* what; double t0; bool on;
@@ -227,9 +239,14 @@ void hshell_apply_sharded(HShell*, double* d_x, double* d_y);
 
 struct EigsOpts { double tol = 1e-8; int ncv = 16; int max_it = 0; unsigned long long seed = 20261018ULL; };
 struct EigsStats { long long nmatvec = 0, nrestart = 0; double resid = 0; int converged = 0; };
-double eigs_smallest(HShell*, const EigsOpts&, double* d_psi, EigsStats*);
+/* d_init: optional start vector of the global length (device; every rank holds all of it), else a seeded random one */
+double eigs_smallest(HShell*, const EigsOpts&, double* d_psi, EigsStats*, const double* d_init = nullptr);
 
 void truncate(const Kron*, const double* d_psi, long long mstates, XForm** L, XForm** R);
 Block* rotate(const Block* enl, const XForm* xf);
+
+/* predict.cpp: wave-function transformation (extension; the reference always starts from a random vector) */
+Wave* wave_create(const Kron*, const double* d_psi, const XForm* grown_side, bool grow_left);
+bool wave_apply(const Wave*, const XForm* shrinking_side, const Block* site, const Kron* new_kron, double* d_psi_new);
 
 }  // namespace dmrgx

@@ -47,7 +47,7 @@ static void small_sym_eig(int n, std::vector<double> A, std::vector<double>& w, 
     S.swap(S2);
 }
 
-double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* stats_out) {
+double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* stats_out, const double* d_init) {
     Ctx* ctx = H->ctx;
     dev::Stream* st = ctx->st;
     /* Multi-GPU: every rank keeps only its own rows [R0, R0+N) of the Krylov basis; the matvec all-gathers the current
@@ -81,9 +81,21 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
     std::vector<double> T((size_t)ld * ld, 0.0);
 
     Trace tr(ctx, "eigs");
-    dev::fill_random(st, V, N, opts.seed, R0); /* element i depends on (seed, global index) only: same start vector on any number of GPUs */
-    dev::dot(st, V, V, N, d_nrm2);
-    dev::allreduce_sum(st, d_nrm2, 1);
+    bool have_start = false;
+    if (d_init) { /* a caller-supplied start vector (wave-function prediction); unusable (zero, not finite) -> the random one */
+        dev::d2d(st, V, d_init + R0, (size_t)N * 8);
+        dev::dot(st, V, V, N, d_nrm2);
+        dev::allreduce_sum(st, d_nrm2, 1);
+        double n2 = 0;
+        dev::d2h(st, &n2, d_nrm2, 8);
+        dev::sync(st);
+        have_start = std::isfinite(n2) && n2 > 1e-200;
+    }
+    if (!have_start) {
+        dev::fill_random(st, V, N, opts.seed, R0); /* element i depends on (seed, global index) only: same start vector on any number of GPUs */
+        dev::dot(st, V, V, N, d_nrm2);
+        dev::allreduce_sum(st, d_nrm2, 1);
+    }
     dev::scale_inv_norm(st, V, d_nrm2, V, N);
 
     const char* early_env = getenv("DMRGX_EARLY_TEST_MIN"); /* test hook: the size above which the in-cycle stopping test is on */
@@ -92,7 +104,9 @@ double eigs_smallest(HShell* H, const EigsOpts& opts, double* d_psi, EigsStats* 
        (profiles/r2_multigpu.md) */
     /* (on several GPUs the round trip is dearer still — the NCCL operations of the next step are enqueued by the host after it —
        so the bar is twenty times higher there) */
-    const bool early_test = early_env ? NG >= atoll(early_env) : (NG >= 50000LL && H->alg_flops >= (dist ? 2e11 : 1e10));
+    /* (a solve started from a predicted vector converges within a few steps of its first cycle: there the test pays from a
+       tenth of that matvec size on) */
+    const bool early_test = early_env ? NG >= atoll(early_env) : (NG >= 50000LL && H->alg_flops >= (dist ? 2e11 : (have_start ? 1e9 : 1e10)));
     int nc = ld, k = 0;
     double theta = 0, resid = 0;
     for (long long it = 0; it < max_it; ++it) {

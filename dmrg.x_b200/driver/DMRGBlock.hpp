@@ -53,6 +53,8 @@ public:
     /** take ownership of a device block produced by the library (enlargement, rotation) */
     PetscErrorCode Adopt(dmrgx_block b) {
         h = std::shared_ptr<dmrgx_block_s>(b, [](dmrgx_block p) { if (p) dmrgx_block_destroy(p); });
+        static long long next_serial = 0;
+        serial = ++next_serial; /* identity of this block's contents (copies share it): -wavefunction_prediction checks that blocks chain up */
         dmrgx_int ns, nst, nsec;
         DMRGX_CALL(dmrgx_block_info(b, &ns, &nst, &nsec));
         num_sites = ns; num_states = nst;
@@ -63,6 +65,7 @@ public:
         return 0;
     }
     PetscBool Initialized() const { return init; }
+    long long Serial() const { return serial; }
     MPI_Comm MPIComm() const { return 0; }
     PetscInt NumSites() const { return num_sites; }
     PetscInt NumStates() const { return num_states; }
@@ -100,6 +103,7 @@ private:
     std::shared_ptr<dmrgx_block_s> h;
     PetscBool init = PETSC_FALSE, mpi_init = PETSC_FALSE;
     PetscInt num_sites = 0, num_states = 0;
+    long long serial = 0;
 };
 
 }  // namespace Block

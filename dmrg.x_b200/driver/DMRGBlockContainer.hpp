@@ -15,6 +15,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <set>
 
 #include "DMRGBlockIO.hpp"
@@ -98,6 +99,9 @@ public:
         if (num_sites < 2) SETERRQ1(mpi_comm, 1, "There must be at least two total sites. Got %lld.", LLD(num_sites));
         if (num_sites % 2) SETERRQ1(mpi_comm, 1, "Total number of sites must be even. Got %lld.", LLD(num_sites));
 
+        /* EXTENSION, off by default: start every sweep step's eigen-solve from the transformed ground state of the previous step
+           (csrc/predict.cpp) instead of the random vector the reference uses (:1484-1500) */
+        o.GetBool("-wavefunction_prediction", &do_prediction, NULL);
         o.GetBool("-verbose", &verbose, NULL); if (o.Has("-verbose") && o.kv["-verbose"].empty()) verbose = PETSC_TRUE;
         o.GetBool("-no_symm", &no_symm, NULL);
         o.GetBool("-do_shell", &do_shell, NULL);
@@ -180,6 +184,8 @@ public:
     /** :590-624 */
     PetscErrorCode Destroy() {
         if (!init) return 0;
+        ClearPendingWaves();
+        sys_bt.clear();
         SingleSite.Destroy();
         for (Block& blk : sys_blocks) blk.Destroy();
         fprintf(fp_step, "\n  ]\n}\n"); fclose(fp_step);
@@ -230,6 +236,7 @@ public:
             std::cout << "Loading blocks from file..." << std::endl;
             if (num_sys_blocks != num_sites - 1) SETERRQ(mpi_comm, 1, "Sweep.dat does not belong to this lattice (num_sys_blocks).");
             sys_blocks.resize((size_t)num_sys_blocks);
+            sys_bt.assign((size_t)num_sys_blocks, nullptr); sys_bt_src.assign((size_t)num_sys_blocks, -2);
             for (PetscInt iblock = 0; iblock < sys_ninit; ++iblock) {
                 const std::string path_read = restart_dir + BlockDir("Sys", iblock);
                 std::cout << "  Reading Block " << iblock << " from: " << path_read << std::endl;
@@ -243,6 +250,7 @@ public:
         printf("WARMUP\n");
         num_sys_blocks = num_sites - 1;
         sys_blocks.resize((size_t)num_sys_blocks);
+        sys_bt.assign((size_t)num_sys_blocks, nullptr); sys_bt_src.assign((size_t)num_sys_blocks, -2);
         for (Block& b : sys_blocks) { ierr = b.Initialize(mpi_comm); CHKERRQ(ierr); }
         ierr = sys_blocks[(size_t)sys_ninit++].Initialize(mpi_comm, 1, PETSC_DEFAULT); CHKERRQ(ierr);
         if (AddSite.NumSites() != 1) SETERRQ1(mpi_comm, 1, "Routine assumes an additional site of 1. Got %lld.", LLD(AddSite.NumSites()));
@@ -443,7 +451,24 @@ private:
         PetscScalar gse_r = 0;
         dmrgx_eigs_stats eps_stats;
         eps_opts.seed = 20261018ULL + (unsigned long long)GlobIdx;
-        DMRGX_CALL(dmrgx_eigs_smallest(H.h, &eps_opts, &gse_r, gsv_r.d, &eps_stats));
+        /* -wavefunction_prediction: the previous step's ground state carried over to this superblock, when the blocks chain up */
+        Vec guess;
+        PetscBool predicted = PETSC_FALSE;
+        const long long idx_sys = BlockIndex(SysBlock), idx_env = BlockIndex(EnvBlock);
+        if (do_prediction && (pending.wL || pending.wR)) {
+            int ok = 0;
+            ierr = MatCreateVecs(H, &guess); CHKERRQ(ierr);
+            if (pending.wL && pending.out_sys == SysBlock.Serial() && pending.xe_left && pending.xe_left_src == EnvBlock.Serial()) {
+                DMRGX_CALL(dmrgx_wave_apply(pending.wL, pending.xe_left->h, AddSite.Handle(), KronBlocks.Handle(), guess.d, &ok));
+            } else if (pending.wR && pending.out_env == EnvBlock.Serial() && pending.xe_right && pending.xe_right_src == SysBlock.Serial()) {
+                DMRGX_CALL(dmrgx_wave_apply(pending.wR, pending.xe_right->h, AddSite.Handle(), KronBlocks.Handle(), guess.d, &ok));
+            }
+            predicted = PetscBool(ok != 0);
+            if (predicted) ++steps_predicted;
+        }
+        ClearPendingWaves();
+        DMRGX_CALL(dmrgx_eigs_smallest_from(H.h, &eps_opts, predicted ? guess.d : NULL, &gse_r, gsv_r.d, &eps_stats));
+        if (guess.d) { ierr = VecDestroy(&guess); CHKERRQ(ierr); }
         step_data.GSEnergy = gse_r;
         total_matvecs += eps_stats.nmatvec;
         double h_bytes = 0, h_flops = 0;
@@ -458,12 +483,23 @@ private:
         if (no_symm) SETERRQ(mpi_comm, PETSC_ERR_SUP, "Unsupported option: no_symm.");
 
         /* reduced density matrices and the rotation */
-        BasisTransformation BT_L, BT_R;
+        std::shared_ptr<BasisTransformation> pBT_L = std::make_shared<BasisTransformation>(), pBT_R = std::make_shared<BasisTransformation>();
+        BasisTransformation &BT_L = *pBT_L, &BT_R = *pBT_R;
         DMRGX_CALL(dmrgx_truncate(KronBlocks.Handle(), gsv_r.d, MStates, &BT_L.h, &BT_R.h));
         ierr = BT_L.Load(); CHKERRQ(ierr);
         ierr = BT_R.Load(); CHKERRQ(ierr);
         ierr = SaveEntanglementSpectra(BT_L, SysBlockEnl.Magnetization.List(), BT_R, EnvBlockEnl.Magnetization.List()); CHKERRQ(ierr);
         ierr = CalculateCorrelations_BlockDiag(KronBlocks, gsv_r, do_measurements); CHKERRQ(ierr);
+        if (do_prediction) {
+            /* both candidates: which block grows in the next step is the caller's business (the left one in the first half of a sweep,
+               the right one in the second, :996-1088); the transformations that created this step's input blocks are captured now,
+               before this step's outputs replace entries of sys_bt */
+            DMRGX_CALL(dmrgx_wave_create(KronBlocks.Handle(), gsv_r.d, BT_L.h, 1, &pending.wL));
+            if (!flg) DMRGX_CALL(dmrgx_wave_create(KronBlocks.Handle(), gsv_r.d, BT_R.h, 0, &pending.wR));
+            if (idx_env >= 0) { pending.xe_left = sys_bt[(size_t)idx_env]; pending.xe_left_src = sys_bt_src[(size_t)idx_env]; }
+            if (idx_sys >= 0) { pending.xe_right = sys_bt[(size_t)idx_sys]; pending.xe_right_src = sys_bt_src[(size_t)idx_sys]; }
+        }
+        const long long serial_sys_in = SysBlock.Serial(), serial_env_in = EnvBlock.Serial();
         ierr = VecDestroy(&gsv_r); CHKERRQ(ierr);
         const double trdms = Tick();
         timings_data.tRdms = trdms - tdiag;
@@ -475,6 +511,13 @@ private:
         if (!flg) DMRGX_CALL(dmrgx_rotate(EnvBlockEnl.Handle(), BT_R.h, &newenv));
         ierr = SysBlockOut.Adopt(newsys); CHKERRQ(ierr);
         if (!flg) { ierr = EnvBlockOut.Adopt(newenv); CHKERRQ(ierr); }
+        if (do_prediction) {
+            const long long osys = BlockIndex(SysBlockOut), oenv = BlockIndex(EnvBlockOut);
+            if (osys >= 0) { sys_bt[(size_t)osys] = pBT_L; sys_bt_src[(size_t)osys] = serial_sys_in; }
+            if (!flg && oenv >= 0) { sys_bt[(size_t)oenv] = pBT_R; sys_bt_src[(size_t)oenv] = serial_env_in; }
+            pending.out_sys = SysBlockOut.Serial();
+            pending.out_env = flg ? -1 : EnvBlockOut.Serial();
+        }
         step_data.NumStates_SysRot = SysBlockOut.NumStates();
         step_data.NumStates_EnvRot = EnvBlockOut.NumStates();
         step_data.TruncErr_Sys = BT_L.TruncErr;
@@ -661,7 +704,7 @@ private:
         for (size_t i = 0; i < sweeps_mstates.size(); ++i) fprintf(fp_data, "%s %lld", i ? "," : "", LLD(sweeps_mstates[i]));
         fprintf(fp_data, " ],\n    \"Seconds\": [");
         for (size_t i = 0; i < sweeps_seconds.size(); ++i) fprintf(fp_data, "%s %.9g", i ? "," : "", sweeps_seconds[i]);
-        fprintf(fp_data, " ]\n  },\n  \"NumMatVecs\": %lld,\n  \"MatVecFlops\": %.6g", LLD(total_matvecs), total_matvec_flops);
+        fprintf(fp_data, " ]\n  },\n  \"NumMatVecs\": %lld,\n  \"MatVecFlops\": %.6g,\n  \"StepsWithPredictedStart\": %lld", LLD(total_matvecs), total_matvec_flops, steps_predicted);
         fflush(fp_data);
         return 0;
     }
@@ -694,6 +737,25 @@ private:
     std::vector<PetscReal> trunc_err;
     double t0abs = 0.0;
     dmrgx_eigs_opts eps_opts = {1e-8, 16, 0, 20261018ULL}; /* SLEPc defaults: tol 1e-8, ncv 16 */
+    /* -wavefunction_prediction (extension): per block the transformation that created it and the serial of the block it enlarged */
+    PetscBool do_prediction = PETSC_FALSE;
+    std::vector<std::shared_ptr<BasisTransformation>> sys_bt;
+    std::vector<long long> sys_bt_src;
+    struct PendingWaves {
+        dmrgx_wave wL = nullptr, wR = nullptr;
+        long long out_sys = -1, out_env = -1, xe_left_src = -2, xe_right_src = -2;
+        std::shared_ptr<BasisTransformation> xe_left, xe_right;
+    } pending;
+    long long steps_predicted = 0;
+    void ClearPendingWaves() {
+        if (pending.wL) dmrgx_wave_destroy(pending.wL);
+        if (pending.wR) dmrgx_wave_destroy(pending.wR);
+        pending = PendingWaves();
+    }
+    long long BlockIndex(const Block& b) const {
+        if (sys_blocks.empty() || &b < sys_blocks.data() || &b >= sys_blocks.data() + sys_blocks.size()) return -1;
+        return (long long)(&b - sys_blocks.data());
+    }
     long long total_matvecs = 0, rows_written = 0;
     double total_matvec_flops = 0;
 };

@@ -148,6 +148,24 @@ typedef struct {
 } dmrgx_eigs_opts;
 typedef struct { dmrgx_int nmatvec, nrestart, converged; double resid; } dmrgx_eigs_stats;
 int dmrgx_eigs_smallest(dmrgx_hshell h, const dmrgx_eigs_opts* opts, double* e0, double* d_psi, dmrgx_eigs_stats* stats);
+/* EXTENSION (no reference counterpart: EPSSolve is never given an initial space there).  The same solve started from
+   d_initial (device, global length; on several GPUs every rank passes the whole vector) — the seeded random vector is used
+   when d_initial is NULL, zero or not finite.  Same eigenpair to `tol`, fewer H*psi when the guess is good. */
+int dmrgx_eigs_smallest_from(dmrgx_hshell h, const dmrgx_eigs_opts* opts, const double* d_initial, double* e0, double* d_psi, dmrgx_eigs_stats* stats);
+
+/* ---- EXTENSION: wave-function transformation (S. R. White, PRL 77, 3633 (1996)) — the guess for dmrgx_eigs_smallest_from.
+   The reference has none (include/DMRGBlockContainer.hpp:1484-1500 starts every step from a random vector); the driver uses this
+   only under -wavefunction_prediction 1.
+     dmrgx_wave_create : after dmrgx_truncate of a step — psi of superblock k with the side that grows in the next step projected
+                         on its kept states (grown_side = that side's dmrgx_xform; grow_left != 0: the left block grows).
+     dmrgx_wave_apply  : in the next step — shrinking_side = the dmrgx_xform that CREATED the other block of the previous step
+                         from the block now in its place, site = the single-site block, k_new = the new superblock.  Writes
+                         the guess (global length of k_new) and *ok = 1, or *ok = 0 when the sector structures do not chain up
+                         (first step of a sweep, blocks replaced in between): the caller then starts from the random vector. */
+typedef struct dmrgx_wave_s* dmrgx_wave;
+int dmrgx_wave_create(dmrgx_kron k, const double* d_psi, dmrgx_xform grown_side, int grow_left, dmrgx_wave* out);
+int dmrgx_wave_apply(dmrgx_wave w, dmrgx_xform shrinking_side, dmrgx_block site, dmrgx_kron k_new, double* d_psi_new, int* ok);
+int dmrgx_wave_destroy(dmrgx_wave w);
 
 /* ---- truncation: GetTruncation, include/DMRGBlockContainer.hpp:1656-1959 ---- */
 int dmrgx_truncate(dmrgx_kron k, const double* d_psi, dmrgx_int mstates, dmrgx_xform* left, dmrgx_xform* right);

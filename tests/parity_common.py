@@ -309,3 +309,88 @@ def check_testkron01_operator_rows(P, ctx, golden_dir):
         assert got == exp, (key, r, got, exp)
         seen += 1
     assert len(ops) == 10 and seen == len(fx["expected"]) == 120
+
+
+def run_sweeps_with_prediction(P, ctx, ham, m_list, tol=1e-10, use_guess=True):
+    """The reference's warm-up and sweep schedule (include/DMRGBlockContainer.hpp:809-840, 996-1088) on the product, with the
+    wave-function transformation of csrc/predict.cpp evaluated at every step: returns one record per sweep step
+    {guess: bool, overlap, nmatvec, energy}.  `use_guess=False` still computes the prediction (for the overlap) but starts the
+    eigen-solve from the random vector, as the reference does."""
+    N = ham["Lx"] * ham["Ly"]
+    def terms(n):
+        return P.HamiltonianTerms(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, ham.get("bcx", 0), ham.get("bcy", 1))
+    site = P.Block.SingleSite(ctx)
+    serial = [0]
+    blocks, bts = {}, {}          # index -> (Block, serial) ; index -> (BasisTransformation, serial of the block it enlarged)
+    def put(idx, blk, bt, src_serial):
+        serial[0] += 1
+        blocks[idx] = (blk, serial[0])
+        bts[idx] = (bt, src_serial)
+        return serial[0]
+    blocks[0] = (site, 0)
+    pending = {}
+    records = []
+
+    def step(insys, inenv, outsys, outenv, m, in_sweep):
+        (bs, ss), (be, se) = blocks[insys], blocks[inenv]
+        L = P.KronEye_Explicit(bs, site, terms(insys + 2))
+        R = P.KronEye_Explicit(be, site, terms(inenv + 2))
+        kb = P.KronBlocks(L, R, [0.0])
+        sh = kb.KronSumConstruct(terms(insys + inenv + 4))
+        guess = None
+        if in_sweep and pending:
+            if pending["out_sys"] == ss and pending["xe_left"] is not None and pending["xe_left"][1] == se:
+                guess = pending["wL"].apply(pending["xe_left"][0], site, kb)
+            elif pending["out_env"] == se and pending["xe_right"] is not None and pending["xe_right"][1] == ss:
+                guess = pending["wR"].apply(pending["xe_right"][0], site, kb)
+        e, psi, st = sh.EPSSolve(tol=tol, initial=guess if use_guess else None)
+        assert st["converged"]
+        if in_sweep:
+            rec = dict(guess=guess is not None, nmatvec=st["nmatvec"], energy=e, overlap=None)
+            if guess is not None:
+                g = guess.get(); x = psi.get()
+                rec["overlap"] = abs(g @ x) / np.linalg.norm(g)
+            records.append(rec)
+        btL, btR = P.GetTruncation(kb, psi, m)
+        xe_left, xe_right = bts.get(inenv), bts.get(insys)   # captured BEFORE this step's outputs replace anything
+        wL, wR = P.Wave(kb, psi, btL, True), P.Wave(kb, psi, btR, False)
+        new_sys = P.RotateOperators(L, btL)
+        s_sys = put(outsys, new_sys, btL, ss)
+        s_env = -1
+        if outsys != outenv:
+            new_env = P.RotateOperators(R, btR)
+            s_env = put(outenv, new_env, btR, se)
+        pending.clear()
+        pending.update(wL=wL, wR=wR, out_sys=s_sys, out_env=s_env, xe_left=xe_left, xe_right=xe_right)
+
+    for n in range(1, N // 2):                                  # warm-up: both blocks grow
+        step(n - 1, n - 1, n, n, m_list[0], False)
+    for m in m_list:
+        pending.clear()
+        for ib in range(N // 2, N - 3):
+            step(ib - 1, N - ib - 3, ib, N - ib - 2, m, True)
+        for ib in range(1, N // 2):
+            step(N - ib - 3, ib - 1, N - ib - 2, ib, m, True)
+    return records
+
+
+def check_wavefunction_prediction(P, ctx):
+    """(1) un-truncated blocks: the transformed vector IS the next ground state (overlap 1): pins every index map of
+    csrc/predict.cpp, both growth directions; (2) truncating sweeps: same energies with and without the guess, fewer H*psi."""
+    ham = dict(Lx=8, Ly=1, J1=0.5, Jz1=1.0, J2=0.0, Jz2=0.0, bcx=0, bcy=0)
+    recs = run_sweeps_with_prediction(P, ctx, ham, [64], tol=1e-12)
+    with_guess = [r for r in recs if r["guess"]]
+    assert len(with_guess) >= len(recs) - 3, [r["guess"] for r in recs]
+    for r in with_guess:
+        assert r["overlap"] > 1.0 - 1e-9, recs
+        assert abs(r["energy"] - (-3.374932598688)) < 1e-9
+    ham = dict(Lx=12, Ly=1, J1=0.5, Jz1=1.0, J2=0.0, Jz2=0.0, bcx=0, bcy=0)
+    a = run_sweeps_with_prediction(P, ctx, ham, [10, 10], tol=1e-10, use_guess=True)
+    b = run_sweeps_with_prediction(P, ctx, ham, [10, 10], tol=1e-10, use_guess=False)
+    assert [r["guess"] for r in a] == [r["guess"] for r in b]
+    for ra, rb in zip(a, b):
+        assert abs(ra["energy"] - rb["energy"]) < 1e-7, (ra, rb)
+    na = sum(r["nmatvec"] for r in a if r["guess"]); nb = sum(r["nmatvec"] for r in b if r["guess"])
+    assert na < 0.7 * nb, (na, nb)
+    assert min(r["overlap"] for r in a if r["guess"]) > 0.9
+    return recs, a, b

@@ -251,3 +251,24 @@ def test_malformed_block_matrix_is_rejected(exe, tmp_path):
     assert r.returncode != 0 and ("invalid row length" in r.stderr or "row lengths" in r.stderr)
     r = restart_with(lambda b: b.__setitem__(slice(12, 16), struct.pack(">i", nz + 1000000)), "huge")
     assert r.returncode != 0 and "shorter than its header" in r.stderr
+
+
+def test_wavefunction_prediction_option(exe, tmp_path):
+    """-wavefunction_prediction 1 (extension; the reference starts every EPSSolve from a random vector): same energies and kept
+    states at every step, most sweep steps start from the transformed previous ground state, fewer H*psi in all."""
+    import json
+    args = ["-Lx", 6, "-Ly", 4, "-J1", 0.5, "-Jz1", 1, "-J2", 0.25, "-Jz2", 0.5, "-do_correlators", 0]
+    runs = []
+    for flag in (0, 1):
+        d = str(tmp_path) + "/p%d/" % flag
+        r = subprocess.run([exe] + [str(a) for a in args] + ["-mwarmup", "16", "-msweeps", "24,32", "-data_dir", d, "-wavefunction_prediction", str(flag)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        runs.append((json.load(open(d + "DMRGRun.json")), json.load(open(d + "DMRGSteps.json"))))
+    (r0, s0), (r1, s1) = runs
+    assert r0["StepsWithPredictedStart"] == 0 and r1["StepsWithPredictedStart"] >= 30          # 40 sweep steps, 2 x 2 without a chain
+    assert r1["NumMatVecs"] < 0.8 * r0["NumMatVecs"]
+    h = s0["headers"]; ie = h.index("GSEnergy")
+    for a, b in zip(s0["table"], s1["table"]):
+        assert abs(a[ie] - b[ie]) < 1e-7 * abs(a[ie]), (a, b)
+        assert a[:ie - 2] == b[:ie - 2] or a[:8] == b[:8]

@@ -206,3 +206,7 @@ def test_argument_validation_at_the_abi(P, ctx):
     with pytest.raises(P.DmrgxError) as e:
         b.set_operator(P.OpSz, 0, [1, 1, 1, 1, 1], [0], [1.0])
     assert e.value.code == 64
+
+
+def test_wavefunction_prediction_extension(P, ctx):
+    pc.check_wavefunction_prediction(P, ctx)
