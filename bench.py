@@ -247,10 +247,12 @@ def reference_arm(args, rank):
     print(json.dumps(line))
 
 
-def run_sweep(args, rank, world, local):
+def run_sweep(args, rank, world, local, predict=False):
     """Seconds per sweep (the metric's second half) through the reference-named executable on the metric's own config
     (BASELINE configs[2]: 12x6 J1-J2 cylinder, -msweeps 512,1024,2048); at N > 1 every rank starts its own process of the
-    executable on its GPU (the executable's ranks find each other through DMRGX_ID_FILE)."""
+    executable on its GPU (the executable's ranks find each other through DMRGX_ID_FILE).  predict: the same run with
+    -wavefunction_prediction 1 (extension: every sweep step's eigen-solve starts from the transformed previous ground state; the
+    reference — and the plain `sweep` section — start from a random vector)."""
     import bench_workload as W
     import tempfile
     exe = os.path.join(ROOT, "dmrg.x_b200", "DMRG-SquareLattice.x")
@@ -264,8 +266,10 @@ def run_sweep(args, rank, world, local):
            "-mwarmup", "128", "-msweeps", msw, "-data_dir", td + "/", "-do_correlators", "0", "-device", str(local)]
     if ham.get("bcx", 0) == 0 and ham.get("bcy", 1) == 0:
         cmd.append("-BCopen")
+    if predict:
+        cmd += ["-wavefunction_prediction", "1"]
     env = dict(os.environ)
-    env["DMRGX_ID_FILE"] = os.path.join(td, "nccl_id_%s" % os.environ.get("DMRGX_BENCH_NONCE", "0"))
+    env["DMRGX_ID_FILE"] = os.path.join(td, "nccl_id_%s%s" % (os.environ.get("DMRGX_BENCH_NONCE", "0"), "p" if predict else ""))
     t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env)
     wall = time.time() - t0
@@ -283,7 +287,9 @@ def run_sweep(args, rank, world, local):
     names = tim["headers"][1:]
     mid = [srow for _, srow in last if srow[ns] == srow[ne]]
     m_last = int(msw.split(",")[-1])
-    return {"config": "%s (BASELINE configs[2]) -mwarmup 128 -msweeps %s, %d GPU(s), default -H_eps_tol 1e-8, correlators off" % (args.config, msw, world),
+    return {"config": "%s (BASELINE configs[2]) -mwarmup 128 -msweeps %s, %d GPU(s), default -H_eps_tol 1e-8, correlators off%s" % (
+                args.config, msw, world, ", -wavefunction_prediction 1 (extension: not the reference's random start)" if predict else ""),
+            "steps_with_predicted_start": run.get("StepsWithPredictedStart", 0),
             "m": m_last, "seconds_per_sweep": run["Sweeps"]["Seconds"][-1], "all_sweeps_seconds": run["Sweeps"]["Seconds"], "steps_per_sweep": len(last),
             "phases_s": {nm: float(sum(t[i + 1] for t, _ in last)) for i, nm in enumerate(names)},
             "energy_midpoint": mid[0][hs.index("GSEnergy")] if mid else None, "energy_last_step": steps["table"][-1][hs.index("GSEnergy")],
@@ -535,6 +541,13 @@ def main():
             sweep = {"error": repr(exc)}
         if world > 1:
             dist.barrier()
+        try:
+            sweep_pred = run_sweep(args, rank, world, local, predict=True)
+        except Exception as exc:
+            sweep_pred = {"error": repr(exc)}
+        if world > 1:
+            dist.barrier()
+        line["sweep_wavefunction_prediction"] = sweep_pred
     line["sweep"] = sweep
     if rank == 0:
         print(json.dumps(line))

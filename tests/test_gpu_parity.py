@@ -372,3 +372,9 @@ def test_testkron01_operator_rows_on_the_product(P, ctx, golden_dir):
 def test_frozen_step_fixture(P, ctx, golden_dir):
     """the CUDA path against committed numbers (no oracle involved at test time)"""
     pc.check_step_fixture(P, ctx, golden_dir)
+
+
+def test_wavefunction_prediction_extension(P, ctx):
+    """csrc/predict.cpp on the device: exact overlap on un-truncated blocks (both growth directions), same energies and fewer
+    H*psi on truncating sweeps"""
+    pc.check_wavefunction_prediction(P, ctx)
