@@ -76,6 +76,13 @@ def main():
     ph = psi.get()
     out["e0"] = e0; out["e_ref"] = e_ref; out["converged"] = st["converged"]; out["nmatvec"] = st["nmatvec"]
     out["overlap"] = float(abs(ph @ psi_ref)); out["norm"] = float(np.linalg.norm(ph))
+    # --- the same solve started from a caller's vector (extension, dmrgx_eigs_smallest_from): a perturbed copy of the ground state,
+    #     whole vector on every rank, each rank takes its own rows
+    rng2 = np.random.default_rng(5)
+    g = psi_ref + 1e-3 * rng2.standard_normal(n) / np.sqrt(n)
+    e1, psi1, st1 = wl.shell.EPSSolve(tol=1e-12, initial=ctx.vec(n, 3.0 * g))
+    out["e0_from"] = e1; out["nmatvec_from"] = st1["nmatvec"]; out["converged_from"] = st1["converged"]
+    out["overlap_from"] = float(abs(psi1.get() @ psi_ref))
     # --- distributed truncation + rotation on the same vector as the oracle
     pd = ctx.vec(n, psi_ref)
     for mk in range(mkeep, mkeep + 8):

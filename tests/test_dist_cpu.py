@@ -47,8 +47,10 @@ def test_sharded_path_matches_oracle(world, config, m):
         assert r["matvec_err"] < 1e-12 and r["host_err"] < 1e-12
         assert r["converged"] and abs(r["e0"] - r["e_ref"]) <= 1e-10 * abs(r["e_ref"])
         assert abs(r["overlap"] - 1.0) < 1e-8 and abs(r["norm"] - 1.0) < 1e-12
+        assert r["converged_from"] and abs(r["e0_from"] - r["e_ref"]) <= 1e-10 * abs(r["e_ref"]) and abs(r["overlap_from"] - 1.0) < 1e-8
+        assert r["nmatvec_from"] <= r["nmatvec"]
         assert r["sectors_ok"] and abs(r["trunc_err"][0] - r["trunc_err"][1]) < 1e-12
         assert r["rot_H_err"] < 1e-11 and r["rot_Sp_err"] < 1e-11
         assert abs(r["expect"] - r["expect_ref"]) < 1e-12
     # all ranks took identical decisions
-    assert len({(r["e0"], r["nmatvec"]) for r in res}) == 1
+    assert len({(r["e0"], r["nmatvec"], r["e0_from"], r["nmatvec_from"]) for r in res}) == 1
