@@ -394,3 +394,31 @@ def check_wavefunction_prediction(P, ctx):
     assert na < 0.7 * nb, (na, nb)
     assert min(r["overlap"] for r in a if r["guess"]) > 0.9
     return recs, a, b
+
+
+def check_wavefunction_prediction_rejects_mismatch(P, ctx):
+    """dmrgx_wave_apply must answer ok = 0 (no exception, nothing written that a caller would use) when the transformation
+    handed in does not chain the previous superblock to the new one, and dmrgx_wave_create must refuse a transformation of
+    the wrong side."""
+    ham = dict(Lx=8, Ly=1, J1=0.5, Jz1=1.0, J2=0.0, Jz2=0.0, bcx=0, bcy=0)
+    def terms(n):
+        return P.HamiltonianTerms(ham["Lx"], ham["Ly"], ham["J1"], ham["Jz1"], ham["J2"], ham["Jz2"], n, 0, 0)
+    site = P.Block.SingleSite(ctx)
+    b1 = P.KronEye_Explicit(site, site, terms(2))            # two sites, exact
+    kb22 = P.KronBlocks(P.KronEye_Explicit(b1, site, terms(3)), P.KronEye_Explicit(b1, site, terms(3)), [0.0])   # 3 + 3 sites
+    e, psi, st = kb22.KronSumConstruct(terms(6)).EPSSolve(tol=1e-12)
+    btL, btR = P.GetTruncation(kb22, psi, 6)                  # truncating: 8 -> 6 states
+    w = P.Wave(kb22, psi, btL, True)
+    # a superblock that does not follow from this one: (2 + 1) + (1 + 1) sites
+    kb_other = P.KronBlocks(P.KronEye_Explicit(b1, site, terms(3)), P.KronEye_Explicit(site, site, terms(2)), [0.5])
+    assert w.apply(btR, site, kb_other) is None
+    assert w.apply(btL, site, kb22) is None
+    # the left transformation of an asymmetric superblock is not a transformation of its right block
+    kb32 = P.KronBlocks(P.KronEye_Explicit(b1, site, terms(3)), P.KronEye_Explicit(site, site, terms(2)), [0.5])
+    e2, psi2, _ = kb32.KronSumConstruct(terms(5)).EPSSolve(tol=1e-12)
+    bl, br = P.GetTruncation(kb32, psi2, 4)
+    try:
+        P.Wave(kb32, psi2, bl, False)
+        raise AssertionError("wave_create accepted the transformation of the other side")
+    except P.DmrgxError as exc:
+        assert exc.code == 62

@@ -210,3 +210,4 @@ def test_argument_validation_at_the_abi(P, ctx):
 
 def test_wavefunction_prediction_extension(P, ctx):
     pc.check_wavefunction_prediction(P, ctx)
+    pc.check_wavefunction_prediction_rejects_mismatch(P, ctx)
