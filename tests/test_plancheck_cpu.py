@@ -77,7 +77,7 @@ def test_kron_bookkeeping_all_sectors_testkron01(P, ctx, orc, golden_dir):
     oL = _block_from_fixture(orc, fx["blocks"]["Left"]); oR = _block_from_fixture(orc, fx["blocks"]["Right"])
     pL = P.Block.Initialize(ctx, 3, fx["blocks"]["Left"]["qn"], fx["blocks"]["Left"]["sizes"])
     pR = P.Block.Initialize(ctx, 2, fx["blocks"]["Right"]["qn"], fx["blocks"]["Right"]["sizes"])
-    for qn in ([], [0.5], [0.5, -0.5], [2.5]):
+    for qn in ([], [0.5], [0.5, -0.5], [2.5], [7.5]):   # [7.5]: no such sector — an empty KronBlocks_t is legal in the reference (include/DMRGKron.hpp:160-171)
         pc.check_kron_bookkeeping(P, orc, P.KronBlocks(pL, pR, qn), orc.KronBlocks(oL, oR, qn))
 
 
